@@ -1,0 +1,112 @@
+"""In-tree build of the mcb200 shared libraries (nvcc cross-compiles sm_100a without a GPU).
+
+Outputs, all under montecarlocuda_b200/lib/ (git-ignored, shipped to the GPU box by gpurun):
+  libmcb200.so                    kernels + engine + extended C ABI (include/mcb200.h)
+  libmcb200_{dp,sp}[_nN].so       the reference's dev_* entry points (include/MonteCarlo.h),
+                                  one per precision and basket width N in {3, 10, 64}
+  pipe_peaks                      FMA / DFMA / MUFU / integer pipe micro-benchmark (bench evidence)
+
+Run as `python -m montecarlocuda_b200.build` or through `__graft_entry__.build()`.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+LIB = PKG / "lib"
+OBJ = PKG / "build"
+INCLUDE = ROOT / "include"
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + ARCH
+
+CUDA_UNITS = ["kernels_vanilla.cu", "kernels_basket.cu", "kernels_cva.cu", "kernels_debug.cu", "engine.cu"]
+HEADERS = ["device_common.cuh", "device_math.cuh", "launch.h", "table_lock.h"]
+DROPIN_WIDTHS = (3, 10, 64)
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the mcb200 libraries cannot be built (there is no CPU build)")
+
+
+def _newer(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print("  $", " ".join(str(c) for c in cmd), flush=True)
+    res = subprocess.run([str(c) for c in cmd], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"build step failed ({res.returncode}): {' '.join(map(str, cmd))}\n{res.stdout}\n{res.stderr}")
+    return res
+
+
+def build(verbose: bool = False, force: bool = False) -> Path:
+    """Compile every CUDA translation unit for sm_100a and link the shared libraries."""
+    nvcc = _nvcc()
+    LIB.mkdir(exist_ok=True)
+    OBJ.mkdir(exist_ok=True)
+    common_deps = [CSRC / h for h in HEADERS] + [INCLUDE / "mcb200.h", Path(__file__)]
+
+    jobs = []
+    objects = []
+    for unit in CUDA_UNITS:
+        src = CSRC / unit
+        obj = OBJ / (Path(unit).stem + ".o")
+        objects.append(obj)
+        if force or _newer(obj, [src] + common_deps):
+            jobs.append([nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", src, "-o", obj])
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+            list(pool.map(lambda c: _run(c, verbose), jobs))
+
+    core = LIB / "libmcb200.so"
+    if force or _newer(core, objects):
+        _run([nvcc, "-shared"] + ARCH + ["-o", core] + objects, verbose)
+
+    # the reference's entry points: thin host-only shims, one per (precision, N)
+    shim_src = CSRC / "dropin.cpp"
+    shim_deps = [shim_src, INCLUDE / "MonteCarlo.h", INCLUDE / "mcb200.h", Path(__file__)]
+    cxx = shutil.which("g++") or "g++"
+    for prec, define in (("dp", []), ("sp", ["-DMCB200_SINGLE"])):
+        for n in DROPIN_WIDTHS:
+            name = f"libmcb200_{prec}.so" if n == 3 else f"libmcb200_{prec}_n{n}.so"
+            out = LIB / name
+            if force or _newer(out, shim_deps + [core]):
+                _run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", f"-DN={n}"] + define +
+                     ["-I", INCLUDE, shim_src, "-o", out, f"-L{LIB}", "-lmcb200", "-Wl,-rpath,$ORIGIN"], verbose)
+
+    peaks_src = CSRC / "pipe_peaks.cu"
+    if peaks_src.exists():
+        peaks = LIB / "pipe_peaks"
+        if force or _newer(peaks, [peaks_src, Path(__file__)]):
+            _run([nvcc, "-O3", "-std=c++17", "-lineinfo"] + ARCH + [peaks_src, "-o", peaks], verbose)
+    return core
+
+
+def build_oracle(verbose: bool = False) -> None:
+    """Build the CPU oracle (test infrastructure) and, when the reference sources are mounted,
+    the unmodified reference into oracle/_ref/.  Building the checker is not using it."""
+    _run(["make", "-C", ROOT / "oracle", "oracle"], verbose)
+    if Path("/root/reference/double_precision/MonteCarloHost.c").exists():
+        _run(["make", "-C", ROOT / "oracle", "ref"], verbose)
+
+
+if __name__ == "__main__":
+    build(verbose=True, force="--force" in sys.argv)
+    build_oracle(verbose=True)
+    print("built:", *sorted(p.name for p in LIB.iterdir()))

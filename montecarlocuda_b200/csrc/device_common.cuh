@@ -1,0 +1,221 @@
+// device_common.cuh -- generator, chunk geometry and the order-free reduction shared by the
+// three pricing kernels (sm_100a).
+//
+// Replaces, for every workload, the reference's per-thread XORWOW state + randomSetup kernel
+// (DP/MonteCarloKernel.cu:285-290, :189), its shared-memory tree reduction (:157-176, :200-219,
+// :263-282) and the sequential host sum over blocks (:416-419).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mcb {
+
+constexpr int kThreads = 256;  // threads per CTA == units per chunk round (part of the stream definition)
+constexpr int kWarps = kThreads / 32;
+constexpr int kLanes = 5;
+constexpr int kAccWords = 12;
+
+// Philox4x32-10 round keys, precomputed on the host (key + i * Weyl): read as constant-bank
+// operands of the three-input XOR, so the key schedule costs no instructions per draw.
+struct PhiloxKeys {
+    uint32_t k0[10];
+    uint32_t k1[10];
+};
+
+// What a launch covers.  All of it derives from the JOB (total paths), never from the GPU count.
+struct Geometry {
+    unsigned long long total_paths;
+    unsigned long long chunk_units;   // kThreads * rounds
+    unsigned long long first_chunk;   // this shard
+    unsigned long long n_chunks;
+    int rounds;                       // units per thread per chunk
+    int scale_exp_sum;                // value * 2^e before the integer split
+    int scale_exp_sumsq;
+};
+
+// One Philox4x32-10 block.  The 64-bit products compile to IMAD.WIDE.U32, the mixes to LOP3.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              const PhiloxKeys &K, uint32_t (&out)[4])
+{
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const unsigned long long p0 = (unsigned long long)M0 * c0;
+        const unsigned long long p1 = (unsigned long long)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[i];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[i];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Split a non-negative double, scaled by 2^e, into five 32-bit limbs (a 160-bit fixed-point
+// window) and add them to `lanes`.  Every step is exact except the final truncation below the
+// window's least significant bit, so sums of limbs are order-independent.  Returns false when
+// the value is negative, NaN or does not fit.
+__device__ __forceinline__ bool lanes_add(double value, int scale_exp, unsigned long long *lanes)
+{
+    const double t = scalbn(value, scale_exp);
+    const double th = t * 0x1p-96;
+    if (!(value >= 0.0) || !(th < 0x1p63))
+        return false;
+    const unsigned long long hi = __double2ull_rz(th);
+    const double rem = t - __ull2double_rn(hi) * 0x1p96;
+    const unsigned long long mid = __double2ull_rz(rem * 0x1p-32);
+    const double lo_d = rem - __ull2double_rn(mid) * 0x1p32;
+    const unsigned long long lo = __double2ull_rz(lo_d);
+    lanes[0] += lo;
+    lanes[1] += mid & 0xffffffffull;
+    lanes[2] += mid >> 32;
+    lanes[3] += hi & 0xffffffffull;
+    lanes[4] += hi >> 32;
+    return true;
+}
+
+struct BlockScratch {
+    double s[kWarps];
+    double s2[kWarps];
+    unsigned long long acc[kAccWords];
+};
+
+__device__ __forceinline__ void scratch_init(BlockScratch &sc)
+{
+    if (threadIdx.x < kAccWords)
+        sc.acc[threadIdx.x] = 0ull;
+    __syncthreads();
+}
+
+// Fixed-shape reduction of one chunk: xor butterfly inside each warp (offsets 16..1, every lane
+// ends with the same value), then warps 0..7 in order on thread 0, which turns the chunk partial
+// into integer limbs held in shared memory.  The chunk partial depends only on the chunk's
+// per-path values, not on which CTA, SM or GPU ran it.
+__device__ __forceinline__ void chunk_commit(double s, double s2, unsigned long long n_valid,
+                                             const Geometry &G, BlockScratch &sc)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        sc.s[warp] = s;
+        sc.s2[warp] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double S = sc.s[0], S2 = sc.s2[0];
+#pragma unroll
+        for (int w = 1; w < kWarps; w++) {
+            S += sc.s[w];
+            S2 += sc.s2[w];
+        }
+        bool ok = lanes_add(S, G.scale_exp_sum, sc.acc);
+        ok = lanes_add(S2, G.scale_exp_sumsq, sc.acc + kLanes) && ok;
+        sc.acc[10] += n_valid;
+        if (!ok)
+            sc.acc[11] += 1ull;
+    }
+    __syncthreads();
+}
+
+// After the CTA's last chunk: 12 integer atomics per CTA.  Integer addition is associative, so
+// the device-wide (and, after the all-reduce, job-wide) totals do not depend on arrival order.
+__device__ __forceinline__ void scratch_flush(const BlockScratch &sc, unsigned long long *acc)
+{
+    if (threadIdx.x < kAccWords) {
+        const unsigned long long v = sc.acc[threadIdx.x];
+        if (v != 0ull)
+            atomicAdd(acc + threadIdx.x, v);
+    }
+}
+
+// The pricing kernel skeleton.  W is a workload policy:
+//   W::Real            float or double: the per-path arithmetic type
+//   W::Params          by-value parameter block (constant bank)
+//   W::kUnitPaths      paths served by one draw unit
+//   W::eval(P, unit, v) fills v[kUnitPaths] with the per-path values of draw unit `unit`
+// A CTA walks chunks first_chunk + blockIdx.x, + gridDim.x, ...; thread t of a chunk owns units
+// base + k * 256 + t for k < rounds, in that order, and accumulates value and value^2 in W::Real
+// (short runs: at most rounds * kUnitPaths <= 256 terms) before the fp64 block reduction.
+template <class W>
+__global__ void __launch_bounds__(kThreads, W::kMinBlocks)
+mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_constant__ Geometry G,
+                     unsigned long long *__restrict__ acc)
+{
+    using Real = typename W::Real;
+    __shared__ BlockScratch sc;
+    scratch_init(sc);
+    const unsigned long long last = G.first_chunk + G.n_chunks;
+    for (unsigned long long chunk = G.first_chunk + blockIdx.x; chunk < last; chunk += gridDim.x) {
+        const unsigned long long base = chunk * G.chunk_units;
+        const unsigned long long path_end = (base + G.chunk_units) * (unsigned long long)W::kUnitPaths;
+        Real s = 0, s2 = 0;
+        unsigned long long n_valid;
+        const bool whole = path_end <= G.total_paths;
+        if (whole) {
+            n_valid = G.chunk_units * (unsigned long long)W::kUnitPaths;
+        } else {
+            const unsigned long long path0 = base * (unsigned long long)W::kUnitPaths;
+            n_valid = G.total_paths > path0 ? G.total_paths - path0 : 0ull;
+        }
+        if (whole || W::kUnitPaths == 1) {
+            // one path per unit: the same loop serves the job's last (partial) chunk, so the
+            // (large) estimator body is instantiated once
+#pragma unroll 1
+            for (int k = 0; k < G.rounds; k++) {
+                const unsigned long long unit = base + (unsigned long long)k * kThreads + threadIdx.x;
+                if (W::kUnitPaths == 1 && !whole && unit >= G.total_paths)
+                    break;
+                Real v[W::kUnitPaths];
+                W::eval(P, unit, v);
+#pragma unroll
+                for (int q = 0; q < W::kUnitPaths; q++) {
+                    s += v[q];
+                    s2 = fma(v[q], v[q], s2);
+                }
+            }
+        } else {
+            // the job's last chunk with several paths per unit: mask paths beyond the total
+#pragma unroll 1
+            for (int k = 0; k < G.rounds; k++) {
+                const unsigned long long unit = base + (unsigned long long)k * kThreads + threadIdx.x;
+                if (unit * (unsigned long long)W::kUnitPaths >= G.total_paths)
+                    break;
+                Real v[W::kUnitPaths];
+                W::eval(P, unit, v);
+#pragma unroll
+                for (int q = 0; q < W::kUnitPaths; q++) {
+                    if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths) {
+                        s += v[q];
+                        s2 = fma(v[q], v[q], s2);
+                    }
+                }
+            }
+        }
+        chunk_commit((double)s, (double)s2, n_valid, G, sc);
+    }
+    scratch_flush(sc, acc);
+}
+
+// Per-path values of units [first_unit, first_unit + n_units): the same W::eval as above.
+template <class W>
+__global__ void __launch_bounds__(kThreads)
+mc_paths_kernel(const __grid_constant__ typename W::Params P, unsigned long long first_unit,
+                unsigned long long n_units, typename W::Real *__restrict__ out)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n_units;
+         i += (unsigned long long)gridDim.x * kThreads) {
+        typename W::Real v[W::kUnitPaths];
+        W::eval(P, first_unit + i, v);
+#pragma unroll
+        for (int q = 0; q < W::kUnitPaths; q++)
+            out[i * W::kUnitPaths + q] = v[q];
+    }
+}
+
+}  // namespace mcb

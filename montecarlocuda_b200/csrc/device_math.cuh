@@ -1,0 +1,102 @@
+// device_math.cuh -- in-register uniforms, Box-Muller normals and the scalar special functions
+// of the pricing kernels, in both working precisions (sm_100a).
+//
+// Replaces curand_normal() (float Box-Muller on XORWOW words even in the reference's DP tree,
+// DP/MonteCarloKernel.cu:68,78,250) and the libm calls of callPayoff / basketPayoff /
+// geomBrownian / cnd / device_bsCall (DP/MonteCarloKernel.cu:67-129).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mcb {
+
+// ---- fp32: every transcendental is ONE MUFU op (no denormal fix-up, no range-reduction code) ----
+__device__ __forceinline__ float mufu_lg2(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_sqrt(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_sin(float x)
+{
+    float y;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float mufu_cos(float x)
+{
+    float y;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// 23 random bits under the exponent of 1.0f: f in [1, 2) exactly (one LEA.HI)
+__device__ __forceinline__ float stuffed_unit_f32(uint32_t w)
+{
+    return __uint_as_float(0x3f800000u | (w >> 9));
+}
+
+// Two words -> one Box-Muller pair.  radius: u = 2 - f in (0, 1], r = sqrt(-2 ln u);
+// angle: 2*pi*(f - 1.5) in [-pi, pi) as one FFMA, the range where MUFU.SIN/COS are most accurate.
+// 4 MUFU per pair (LG2, SQRT, SIN, COS).
+__device__ __forceinline__ void box_muller_f32(uint32_t wa, uint32_t wb, float &z0, float &z1)
+{
+    const float u = 2.0f - stuffed_unit_f32(wa);
+    const float r = mufu_sqrt(mufu_lg2(u) * -1.3862943611198906f);  // -2 ln2 * log2(u)
+    const float a = fmaf(stuffed_unit_f32(wb), 6.283185307179586f, -9.42477796076938f);
+    z0 = r * mufu_cos(a);
+    z1 = r * mufu_sin(a);
+}
+
+__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float (&z)[4])
+{
+    box_muller_f32(w[0], w[1], z[0], z[1]);
+    box_muller_f32(w[2], w[3], z[2], z[3]);
+}
+
+// ---- fp64 ----
+// 52 random bits under the exponent of 1.0: f in [1, 2) exactly (one LOP3 + register pairing)
+__device__ __forceinline__ double stuffed_unit_f64(uint32_t w_hi, uint32_t w_lo)
+{
+    return __hiloint2double((int)(0x3ff00000u | (w_hi & 0xfffffu)), (int)w_lo);
+}
+
+// Four words -> one fp64 Box-Muller pair (true 52-bit uniforms; the reference's "double" normals
+// are float).
+__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], double (&z)[2])
+{
+    const double u = 2.0 - stuffed_unit_f64(w[0], w[1]);
+    const double r = sqrt(-2.0 * log(u));
+    const double t = stuffed_unit_f64(w[2], w[3]) - 1.0;  // turn fraction in [0, 1)
+    double sn, cs;
+    sincospi(2.0 * t, &sn, &cs);
+    z[0] = r * cs;
+    z[1] = r * sn;
+}
+
+// precision-generic wrappers used by the workload policies
+__device__ __forceinline__ float exp_real(float x) { return mufu_ex2(x * 1.4426950408889634f); }
+__device__ __forceinline__ double exp_real(double x) { return exp(x); }
+__device__ __forceinline__ float rcp_real(float x) { return mufu_rcp(x); }
+__device__ __forceinline__ double rcp_real(double x) { return 1.0 / x; }
+
+}  // namespace mcb

@@ -1,0 +1,873 @@
+// engine.cu -- host side of libmcb200: persistent context, job planning, host-built parameter
+// tables, shard launches, the exact-integer combine and the closing formulas.
+//
+// Replaces the host orchestration of the reference GPU engine: MonteCarlo_init / MonteCarlo /
+// cvaMonteCarlo / MonteCarlo_closing and the three extern "C" wrappers
+// (DP/MonteCarloKernel.cu:296-532).  The reference allocates device + pinned memory, seeds
+// 65 536 XORWOW states, copies parameters into __constant__ symbols, prints timing lines and
+// frees everything on EVERY call; here a context owns a stream, a 96-byte device accumulator and
+// its pinned mirror for its whole life, the generator is stateless, and a call is
+// memset -> one kernel -> 96-byte copy.
+#include "../../include/mcb200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+
+using namespace mcb;
+
+struct mcb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    unsigned long long *d_acc = nullptr;
+    unsigned long long *h_acc = nullptr;  // pinned
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::string last_error;
+    uint64_t launches = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+class DeviceGuard {
+public:
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&previous_) != cudaSuccess)
+            previous_ = -1;
+        status_ = cudaSetDevice(device);
+    }
+    ~DeviceGuard()
+    {
+        if (previous_ >= 0)
+            cudaSetDevice(previous_);
+    }
+    cudaError_t status() const { return status_; }
+
+private:
+    int previous_ = -1;
+    cudaError_t status_ = cudaSuccess;
+};
+
+int fail_cuda(mcb200_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (ctx) {
+        ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    }
+    cudaGetLastError();  // clear the sticky-free error state
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice)
+               ? MCB200_ERR_NO_DEVICE
+               : MCB200_ERR_CUDA;
+}
+
+int fail(mcb200_ctx *ctx, int status, const char *what)
+{
+    if (ctx)
+        ctx->last_error = what;
+    return status;
+}
+
+#define MCB_CUDA(ctx, call)                                  \
+    do {                                                     \
+        cudaError_t _e = (call);                             \
+        if (_e != cudaSuccess)                               \
+            return fail_cuda((ctx), _e, #call);              \
+    } while (0)
+
+bool finite_all(std::initializer_list<double> xs)
+{
+    for (double x : xs)
+        if (!std::isfinite(x))
+            return false;
+    return true;
+}
+
+PhiloxKeys make_keys(uint64_t seed)
+{
+    // key schedule of Philox4x32-10: round i uses key + i * (W0, W1)
+    PhiloxKeys k;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int i = 0; i < 10; i++) {
+        k.k0[i] = k0;
+        k.k1[i] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return k;
+}
+
+// units per thread per chunk: a pure function of the job size (never of the GPU count), aiming
+// at >= 2^16 chunks for large jobs and at most 64 units per thread
+int chunk_rounds(uint64_t total_units)
+{
+    const uint64_t q = total_units >> 24;
+    int r = 1;
+    while (r < 64 && (uint64_t)(r * 2) <= q)
+        r *= 2;
+    return r;
+}
+
+int fill_plan(int workload, int precision, uint64_t n_paths, double scale_ref, double discount,
+              mcb200_plan_t *plan)
+{
+    if (!plan || n_paths == 0 || (precision != MCB200_F32 && precision != MCB200_F64))
+        return MCB200_ERR_INVALID;
+    if (!(scale_ref > 0) || !std::isfinite(scale_ref) || !std::isfinite(discount))
+        return MCB200_ERR_INVALID;
+    std::memset(plan, 0, sizeof *plan);
+    plan->workload = workload;
+    plan->precision = precision;
+    plan->total_paths = n_paths;
+    plan->unit_paths = workload == MCB200_VANILLA ? (precision == MCB200_F64 ? 2 : 4) : 1;
+    plan->total_units = (n_paths + plan->unit_paths - 1) / plan->unit_paths;
+    plan->rounds = chunk_rounds(plan->total_units);
+    plan->chunk_units = (uint64_t)kThreads * plan->rounds;
+    plan->n_chunks = (plan->total_units + plan->chunk_units - 1) / plan->chunk_units;
+    // fixed-point window: least significant bit 2^-80 of the job's money scale (a power of two
+    // near max(spot, strike)), 160 bits wide
+    const int e = std::ilogb(scale_ref) + 1;
+    plan->scale_exp_sum = 80 - e;
+    plan->scale_exp_sumsq = 80 - 2 * e;
+    plan->discount = discount;
+    return MCB200_OK;
+}
+
+Geometry make_geometry(const mcb200_plan_t &plan, uint64_t first_chunk, uint64_t n_chunks)
+{
+    Geometry g{};
+    g.total_paths = plan.total_paths;
+    g.chunk_units = plan.chunk_units;
+    g.first_chunk = first_chunk;
+    g.n_chunks = n_chunks;
+    g.rounds = plan.rounds;
+    g.scale_exp_sum = plan.scale_exp_sum;
+    g.scale_exp_sumsq = plan.scale_exp_sumsq;
+    return g;
+}
+
+int check_range(const mcb200_plan_t *plan, uint64_t first_chunk, uint64_t n_chunks)
+{
+    if (!plan || first_chunk > plan->n_chunks || n_chunks > plan->n_chunks - first_chunk)
+        return MCB200_ERR_ALIGNMENT;
+    return MCB200_OK;
+}
+
+// ---- host-built jobs --------------------------------------------------------------------------
+
+int make_vanilla_job(int precision, const mcb200_option_t *o, uint64_t seed, VanillaJob *job)
+{
+    if (!o || !finite_all({o->s, o->k, o->r, o->v, o->t}) || !(o->s > 0) || o->v < 0 || o->t < 0)
+        return MCB200_ERR_INVALID;
+    // S_T = S0 exp((r - v^2/2) T + v sqrt(T) z)   (DP/MonteCarloKernel.cu:69)
+    const double unit = precision == MCB200_F32 ? 1.4426950408889634074 : 1.0;
+    job->keys = make_keys(seed);
+    job->a = (std::log(o->s) + (o->r - 0.5 * o->v * o->v) * o->t) * unit;
+    job->b = o->v * std::sqrt(o->t) * unit;
+    job->k = o->k;
+    return MCB200_OK;
+}
+
+struct BasketTables {
+    std::vector<double> factor, a, m;
+    BasketJob job;
+};
+
+int make_basket_job(const mcb200_basket_t *o, uint64_t seed, BasketTables *t)
+{
+    if (!o || !o->s || !o->v || !o->p || !o->d || !o->w)
+        return MCB200_ERR_INVALID;
+    const int n = o->n;
+    if (n < 1)
+        return MCB200_ERR_INVALID;
+    if (n > MCB200_MAX_ASSETS || basket_padded_width(n) == 0)
+        return MCB200_ERR_UNSUPPORTED;
+    if (!finite_all({o->k, o->t, o->r}) || o->t < 0)
+        return MCB200_ERR_INVALID;
+    t->factor.assign((size_t)n * n, 0.0);
+    t->a.assign(n, 0.0);
+    t->m.assign(n, 0.0);
+    bool full = false;
+    const double sqrt_t = std::sqrt(o->t);
+    for (int i = 0; i < n; i++) {
+        if (!finite_all({o->s[i], o->v[i], o->d[i], o->w[i]}))
+            return MCB200_ERR_INVALID;
+        // S_i = s_i exp((r - v_i^2/2) T + v_i sqrt(T) (sum_j p_ij g_j + d_i))  (DP/MonteCarloKernel.cu:79-93)
+        for (int j = 0; j < n; j++) {
+            const double p = o->p[(size_t)i * n + j];
+            if (!std::isfinite(p))
+                return MCB200_ERR_INVALID;
+            if (j > i && p != 0.0)
+                full = true;
+            t->factor[(size_t)i * n + j] = o->v[i] * sqrt_t * p;
+        }
+        t->a[i] = (o->r - 0.5 * o->v[i] * o->v[i]) * o->t + o->v[i] * sqrt_t * o->d[i];
+        t->m[i] = o->w[i] * o->s[i];
+    }
+    t->job.keys = make_keys(seed);
+    t->job.n = n;
+    t->job.full = full;
+    t->job.factor = t->factor.data();
+    t->job.a = t->a.data();
+    t->job.m = t->m.data();
+    t->job.k = o->k;
+    return MCB200_OK;
+}
+
+struct CvaTables {
+    std::vector<CvaDateHost> dates;
+    CvaJob job;
+};
+
+// Remaining time at each exposure date.  grid_mode 0 follows the reference literally: dt = T / n
+// and t -= dt in the WORKING precision, a date contributes when the rounded t is >= 0
+// (DP/MonteCarloKernel.cu:233,249).
+template <typename Real>
+void reference_grid(double T, int n, std::vector<double> &tau, std::vector<int> &keep, double &dt_out)
+{
+    const Real dt = (Real)T / (Real)n;
+    Real t = (Real)T;
+    for (int j = 0; j < n; j++) {
+        t -= dt;
+        tau[j] = (double)t;
+        keep[j] = t >= 0 ? 1 : 0;
+    }
+    dt_out = (double)dt;
+}
+
+int make_cva_job(int precision, const mcb200_cva_t *c, uint64_t seed, CvaTables *t)
+{
+    if (!c)
+        return MCB200_ERR_INVALID;
+    const mcb200_option_t &o = c->option;
+    const int n = c->n_dates;
+    if (!finite_all({o.s, o.k, o.r, o.v, o.t, c->def_int, c->lgd}) || !(o.s > 0) || !(o.k > 0) || !(o.v > 0) ||
+        !(o.t > 0) || n < 1)
+        return MCB200_ERR_INVALID;
+    if (n > MCB200_MAX_DATES)
+        return MCB200_ERR_UNSUPPORTED;
+    std::vector<double> tau(n);
+    std::vector<int> keep(n);
+    double dt;
+    if (c->grid_mode == 0) {
+        if (precision == MCB200_F32)
+            reference_grid<float>(o.t, n, tau, keep, dt);
+        else
+            reference_grid<double>(o.t, n, tau, keep, dt);
+    } else {
+        dt = o.t / n;
+        for (int j = 0; j < n; j++) {
+            tau[j] = o.t * (double)(n - 1 - j) / (double)n;
+            keep[j] = 1;
+        }
+    }
+    int kept = 0;
+    while (kept < n && keep[kept])
+        kept++;
+    const double huge = precision == MCB200_F32 ? 1e30 : 1e300;
+    t->dates.assign(kept > 0 ? kept : 1, CvaDateHost{});
+    for (int j = 0; j < kept; j++) {
+        CvaDateHost &d = t->dates[j];
+        // dp_j = e^{-lambda t_{j-1}} - e^{-lambda t_j}   (DP/MonteCarloKernel.cu:248), times LGD (:259)
+        d.w = c->lgd * (std::exp(-(dt * j) * c->def_int) - std::exp(-(dt * (j + 1)) * c->def_int));
+        if (tau[j] > 0) {
+            // d1 = (ln(s/K) + (r + v^2/2) tau) / (v sqrt(tau)), d2 = d1 - v sqrt(tau)   (:126-127)
+            const double sig = o.v * std::sqrt(tau[j]);
+            d.inv = 1.0 / sig;
+            d.c1 = (o.r + 0.5 * o.v * o.v) * tau[j] * d.inv;
+            d.sig = sig;
+            d.kd = o.k * std::exp(-o.r * tau[j]);
+        } else {
+            // tau == 0: the reference's formulas degenerate to the intrinsic value
+            // (log(s/K)/0 = +-inf, cnd -> 0 or 1); a huge finite slope does the same without NaNs
+            d.inv = huge;
+            d.c1 = 0;
+            d.sig = 0;
+            d.kd = o.k;
+        }
+        d.rkd = 1.0 / d.kd;
+    }
+    t->job.keys = make_keys(seed);
+    t->job.y0 = std::log(o.s / o.k);
+    t->job.mu_dt = (o.r - 0.5 * o.v * o.v) * dt;  // geomBrownian, DP/MonteCarloKernel.cu:104-107
+    t->job.sig_dt = o.v * std::sqrt(dt);
+    t->job.k = o.k;
+    t->job.n_dates = kept;
+    t->job.dates = t->dates.data();
+    return MCB200_OK;
+}
+
+double basket_scale(const mcb200_basket_t *o)
+{
+    double ref = std::fabs(o->k);
+    double gross = 0;
+    for (int i = 0; i < o->n; i++)
+        gross += std::fabs(o->w[i] * o->s[i]);
+    return gross > ref ? gross : ref;
+}
+
+// ---- launching ---------------------------------------------------------------------------------
+
+struct AnyJob {
+    int workload = 0;
+    VanillaJob vanilla;
+    BasketTables basket;
+    CvaTables cva;
+};
+
+int blocks_per_sm(const mcb200_plan_t &plan, const AnyJob &job)
+{
+    switch (plan.workload) {
+        case MCB200_VANILLA: return vanilla_blocks_per_sm(plan.precision);
+        case MCB200_BASKET: return basket_blocks_per_sm(plan.precision, job.basket.job.n, job.basket.job.full);
+        default: return cva_blocks_per_sm(plan.precision);
+    }
+}
+
+// enqueue one shard on `stream` (device already current)
+int enqueue(mcb200_ctx *ctx, const mcb200_plan_t &plan, const AnyJob &job, uint64_t first_chunk,
+            uint64_t n_chunks, unsigned long long *d_acc, cudaStream_t stream)
+{
+    if (n_chunks == 0)
+        return MCB200_OK;
+    int per_sm = blocks_per_sm(plan, job);
+    if (per_sm < 1)
+        return fail(ctx, MCB200_ERR_CUDA, "kernel cannot be resident on this device (occupancy 0)");
+    uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
+    if (grid > n_chunks)
+        grid = n_chunks;
+    const Geometry g = make_geometry(plan, first_chunk, n_chunks);
+    cudaError_t e;
+    switch (plan.workload) {
+        case MCB200_VANILLA: e = vanilla_launch(plan.precision, job.vanilla, g, (int)grid, d_acc, stream); break;
+        case MCB200_BASKET: e = basket_launch(plan.precision, job.basket.job, g, (int)grid, d_acc, stream); break;
+        default: e = cva_launch(plan.precision, job.cva.job, g, (int)grid, d_acc, stream); break;
+    }
+    if (e != cudaSuccess)
+        return fail_cuda(ctx, e, "kernel launch");
+    ctx->launches++;
+    return MCB200_OK;
+}
+
+// one-call pricing over n_ctx devices of this process
+int price(mcb200_ctx **ctxs, int n_ctx, const mcb200_plan_t &plan, const AnyJob &job, mcb200_result_t *out)
+{
+    if (!ctxs || n_ctx < 1 || !out)
+        return MCB200_ERR_INVALID;
+    for (int i = 0; i < n_ctx; i++)
+        if (!ctxs[i])
+            return MCB200_ERR_INVALID;
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int i = 0; i < n_ctx; i++)
+        locks.emplace_back(ctxs[i]->mu);
+    // enqueue everywhere first, then wait: the devices run concurrently
+    for (int i = 0; i < n_ctx; i++) {
+        mcb200_ctx *ctx = ctxs[i];
+        DeviceGuard guard(ctx->device);
+        MCB_CUDA(ctx, guard.status());
+        uint64_t first, count;
+        int st = mcb200_shard_range(&plan, i, n_ctx, &first, &count);
+        if (st != MCB200_OK)
+            return st;
+        MCB_CUDA(ctx, cudaMemsetAsync(ctx->d_acc, 0, sizeof(unsigned long long) * kAccWords, ctx->stream));
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+        st = enqueue(ctx, plan, job, first, count, ctx->d_acc, ctx->stream);
+        if (st != MCB200_OK)
+            return st;
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+        MCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_acc, ctx->d_acc, sizeof(unsigned long long) * kAccWords,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    uint64_t total[MCB200_ACC_WORDS] = {0};
+    double kernel_ms = 0;
+    for (int i = 0; i < n_ctx; i++) {
+        mcb200_ctx *ctx = ctxs[i];
+        DeviceGuard guard(ctx->device);
+        MCB_CUDA(ctx, guard.status());
+        MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        MCB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+        if (ms > kernel_ms)
+            kernel_ms = ms;
+        for (int w = 0; w < MCB200_ACC_WORDS; w++)
+            total[w] += ctx->h_acc[w];  // exact: integer limbs with 31 bits of headroom
+    }
+    int st = mcb200_finalize(&plan, total, out);
+    out->kernel_ms = kernel_ms;
+    if (st != MCB200_OK)
+        return fail(ctxs[0], st, st == MCB200_ERR_OVERFLOW ? "partial sum outside the fixed-point window or NaN"
+                                                           : "path count mismatch");
+    return MCB200_OK;
+}
+
+// per-path values of [first_path, first_path + n_paths)
+int paths(mcb200_ctx *ctx, const mcb200_plan_t &plan, const AnyJob &job, uint64_t first_path, uint64_t n_paths,
+          void *out_host)
+{
+    if (!ctx || !out_host || n_paths == 0)
+        return MCB200_ERR_INVALID;
+    if (first_path % (uint64_t)plan.unit_paths)
+        return fail(ctx, MCB200_ERR_ALIGNMENT, "first_path is not a multiple of the draw-unit size");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    const uint64_t first_unit = first_path / plan.unit_paths;
+    const uint64_t n_units = (n_paths + plan.unit_paths - 1) / plan.unit_paths;
+    const size_t elem = plan.precision == MCB200_F64 ? 8 : 4;
+    void *d_out = nullptr;
+    MCB_CUDA(ctx, cudaMalloc(&d_out, n_units * plan.unit_paths * elem));
+    cudaError_t e;
+    switch (plan.workload) {
+        case MCB200_VANILLA: e = vanilla_paths(plan.precision, job.vanilla, first_unit, n_units, d_out, ctx->stream); break;
+        case MCB200_BASKET: e = basket_paths(plan.precision, job.basket.job, first_unit, n_units, d_out, ctx->stream); break;
+        default: e = cva_paths(plan.precision, job.cva.job, first_unit, n_units, d_out, ctx->stream); break;
+    }
+    if (e == cudaSuccess) {
+        ctx->launches++;
+        e = cudaMemcpyAsync(out_host, d_out, n_paths * elem, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess)
+        return fail_cuda(ctx, e, "per-path kernel");
+    return MCB200_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// public C ABI
+// ================================================================================================
+extern "C" {
+
+int mcb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mcb200_create(mcb200_ctx **out, int device)
+{
+    if (!out)
+        return MCB200_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return MCB200_ERR_NO_DEVICE;  // no CPU fallback: the engine is CUDA or nothing
+    }
+    if (device < 0 || device >= n)
+        return MCB200_ERR_NO_DEVICE;
+    mcb200_ctx *ctx = new (std::nothrow) mcb200_ctx;
+    if (!ctx)
+        return MCB200_ERR_INVALID;
+    ctx->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    bool ok = guard.status() == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&ctx->d_acc, sizeof(unsigned long long) * kAccWords) == cudaSuccess &&
+              cudaMallocHost(&ctx->h_acc, sizeof(unsigned long long) * kAccWords) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        mcb200_destroy(ctx);
+        return MCB200_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return MCB200_OK;
+}
+
+int mcb200_destroy(mcb200_ctx *ctx)
+{
+    if (!ctx)
+        return MCB200_OK;
+    {
+        DeviceGuard guard(ctx->device);
+        if (ctx->stream)
+            cudaStreamSynchronize(ctx->stream);
+        if (ctx->ev_begin)
+            cudaEventDestroy(ctx->ev_begin);
+        if (ctx->ev_end)
+            cudaEventDestroy(ctx->ev_end);
+        if (ctx->d_acc)
+            cudaFree(ctx->d_acc);
+        if (ctx->h_acc)
+            cudaFreeHost(ctx->h_acc);
+        if (ctx->stream)
+            cudaStreamDestroy(ctx->stream);
+        cudaGetLastError();
+    }
+    delete ctx;
+    return MCB200_OK;
+}
+
+int mcb200_device(const mcb200_ctx *ctx) { return ctx ? ctx->device : -1; }
+int mcb200_sm_count(const mcb200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t mcb200_launch_count(const mcb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+const char *mcb200_last_error(const mcb200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+const char *mcb200_strerror(int status)
+{
+    switch (status) {
+        case MCB200_OK: return "success";
+        case MCB200_ERR_INVALID: return "invalid argument";
+        case MCB200_ERR_CUDA: return "CUDA runtime error";
+        case MCB200_ERR_NO_DEVICE: return "no usable CUDA device (mcb200 has no CPU fallback)";
+        case MCB200_ERR_OVERFLOW: return "partial sum outside the fixed-point window, or NaN";
+        case MCB200_ERR_UNSUPPORTED: return "unsupported size";
+        case MCB200_ERR_ALIGNMENT: return "range not aligned to the job's chunk / draw-unit grid";
+        default: return "unknown status";
+    }
+}
+
+// ---- planning ----
+int mcb200_plan_vanilla(int precision, const mcb200_option_t *opt, uint64_t n_paths, mcb200_plan_t *plan)
+{
+    if (!opt || !finite_all({opt->s, opt->k, opt->r, opt->t}))
+        return MCB200_ERR_INVALID;
+    const double ref = std::fabs(opt->s) > std::fabs(opt->k) ? std::fabs(opt->s) : std::fabs(opt->k);
+    // price = e^{-rT} mean   (DP/MonteCarloKernel.cu:420)
+    return fill_plan(MCB200_VANILLA, precision, n_paths, ref, std::exp(-opt->r * opt->t), plan);
+}
+
+int mcb200_plan_basket(int precision, const mcb200_basket_t *opt, uint64_t n_paths, mcb200_plan_t *plan)
+{
+    if (!opt || !opt->s || !opt->w || opt->n < 1 || !finite_all({opt->k, opt->r, opt->t}))
+        return MCB200_ERR_INVALID;
+    return fill_plan(MCB200_BASKET, precision, n_paths, basket_scale(opt), std::exp(-opt->r * opt->t), plan);
+}
+
+int mcb200_plan_cva(int precision, const mcb200_cva_t *cva, uint64_t n_paths, mcb200_plan_t *plan)
+{
+    if (!cva || !finite_all({cva->option.s, cva->option.k}))
+        return MCB200_ERR_INVALID;
+    const double s = std::fabs(cva->option.s), k = std::fabs(cva->option.k);
+    // the CVA is not discounted   (DP/MonteCarloKernel.cu:466)
+    return fill_plan(MCB200_CVA, precision, n_paths, s > k ? s : k, 1.0, plan);
+}
+
+int mcb200_shard_range(const mcb200_plan_t *plan, int rank, int world, uint64_t *first_chunk, uint64_t *n_chunks)
+{
+    if (!plan || !first_chunk || !n_chunks || world < 1 || rank < 0 || rank >= world)
+        return MCB200_ERR_INVALID;
+    const unsigned __int128 n = plan->n_chunks;
+    const uint64_t lo = (uint64_t)(n * (unsigned)rank / (unsigned)world);
+    const uint64_t hi = (uint64_t)(n * (unsigned)(rank + 1) / (unsigned)world);
+    *first_chunk = lo;
+    *n_chunks = hi - lo;
+    return MCB200_OK;
+}
+
+// ---- closing: DP/MonteCarloKernel.cu:412-423 (pricing) and :459-469 (CVA) ----
+static long double lanes_value(const uint64_t *lanes, int scale_exp)
+{
+    uint64_t limb[MCB200_LANES + 1], carry = 0;
+    for (int i = 0; i < MCB200_LANES; i++) {
+        const uint64_t x = lanes[i] + carry;
+        limb[i] = x & 0xffffffffu;
+        carry = x >> 32;
+    }
+    limb[MCB200_LANES] = carry;
+    long double acc = 0;
+    for (int i = MCB200_LANES; i >= 0; i--)
+        acc = acc * 4294967296.0L + (long double)limb[i];
+    return ldexpl(acc, -scale_exp);
+}
+
+int mcb200_finalize(const mcb200_plan_t *plan, const uint64_t acc[MCB200_ACC_WORDS], mcb200_result_t *out)
+{
+    if (!plan || !acc || !out)
+        return MCB200_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    const long double sum = lanes_value(acc, plan->scale_exp_sum);
+    const long double sumsq = lanes_value(acc + MCB200_LANES, plan->scale_exp_sumsq);
+    const long double n = (long double)plan->total_paths;
+    out->n_paths = acc[10];
+    out->sum = (double)sum;
+    out->sumsq = (double)sumsq;
+    out->mean = (double)(sum / n);
+    out->expected = (double)((long double)plan->discount * (sum / n));
+    // s^2 = (n sum(x^2) - sum(x)^2) / (n (n - 1)); Confidence = 1.96 s / sqrt(n) on the UNdiscounted value
+    long double var = (n * sumsq - sum * sum) / (n * (n - 1.0L));
+    if (var < 0)
+        var = 0;
+    const long double sd = sqrtl(var);
+    out->confidence = (double)(1.96L * sd / sqrtl(n));
+    out->std_error = (double)((long double)plan->discount * sd / sqrtl(n));
+    if (acc[11] != 0)
+        return MCB200_ERR_OVERFLOW;
+    if (acc[10] != plan->total_paths)
+        return MCB200_ERR_INVALID;
+    return MCB200_OK;
+}
+
+// ---- sharded launches ----
+int mcb200_vanilla_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_option_t *opt, uint64_t seed,
+                          uint64_t first_chunk, uint64_t n_chunks, uint64_t *d_acc, void *stream)
+{
+    if (!ctx || !plan || !d_acc || plan->workload != MCB200_VANILLA)
+        return MCB200_ERR_INVALID;
+    int st = check_range(plan, first_chunk, n_chunks);
+    if (st != MCB200_OK)
+        return st;
+    AnyJob job;
+    st = make_vanilla_job(plan->precision, opt, seed, &job.vanilla);
+    if (st != MCB200_OK)
+        return st;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
+                   stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int mcb200_basket_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_basket_t *opt, uint64_t seed,
+                         uint64_t first_chunk, uint64_t n_chunks, uint64_t *d_acc, void *stream)
+{
+    if (!ctx || !plan || !d_acc || plan->workload != MCB200_BASKET)
+        return MCB200_ERR_INVALID;
+    int st = check_range(plan, first_chunk, n_chunks);
+    if (st != MCB200_OK)
+        return st;
+    AnyJob job;
+    st = make_basket_job(opt, seed, &job.basket);
+    if (st != MCB200_OK)
+        return st;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
+                   stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int mcb200_cva_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_cva_t *cva, uint64_t seed,
+                      uint64_t first_chunk, uint64_t n_chunks, uint64_t *d_acc, void *stream)
+{
+    if (!ctx || !plan || !d_acc || plan->workload != MCB200_CVA)
+        return MCB200_ERR_INVALID;
+    int st = check_range(plan, first_chunk, n_chunks);
+    if (st != MCB200_OK)
+        return st;
+    AnyJob job;
+    st = make_cva_job(plan->precision, cva, seed, &job.cva);
+    if (st != MCB200_OK)
+        return st;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
+                   stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+// ---- one-call pricing ----
+int mcb200_vanilla_multi(mcb200_ctx **ctxs, int n_ctx, int precision, const mcb200_option_t *opt,
+                         uint64_t n_paths, uint64_t seed, mcb200_result_t *out)
+{
+    mcb200_plan_t plan;
+    int st = mcb200_plan_vanilla(precision, opt, n_paths, &plan);
+    if (st != MCB200_OK)
+        return st;
+    AnyJob job;
+    st = make_vanilla_job(precision, opt, seed, &job.vanilla);
+    if (st != MCB200_OK)
+        return st;
+    return price(ctxs, n_ctx, plan, job, out);
+}
+
+int mcb200_basket_multi(mcb200_ctx **ctxs, int n_ctx, int precision, const mcb200_basket_t *opt,
+                        uint64_t n_paths, uint64_t seed, mcb200_result_t *out)
+{
+    mcb200_plan_t plan;
+    int st = mcb200_plan_basket(precision, opt, n_paths, &plan);
+    if (st != MCB200_OK)
+        return st;
+    AnyJob job;
+    st = make_basket_job(opt, seed, &job.basket);
+    if (st != MCB200_OK)
+        return st;
+    return price(ctxs, n_ctx, plan, job, out);
+}
+
+int mcb200_cva_multi(mcb200_ctx **ctxs, int n_ctx, int precision, const mcb200_cva_t *cva, uint64_t n_paths,
+                     uint64_t seed, mcb200_result_t *out)
+{
+    mcb200_plan_t plan;
+    int st = mcb200_plan_cva(precision, cva, n_paths, &plan);
+    if (st != MCB200_OK)
+        return st;
+    AnyJob job;
+    st = make_cva_job(precision, cva, seed, &job.cva);
+    if (st != MCB200_OK)
+        return st;
+    return price(ctxs, n_ctx, plan, job, out);
+}
+
+int mcb200_vanilla(mcb200_ctx *ctx, int precision, const mcb200_option_t *opt, uint64_t n_paths, uint64_t seed,
+                   mcb200_result_t *out)
+{
+    return mcb200_vanilla_multi(&ctx, 1, precision, opt, n_paths, seed, out);
+}
+
+int mcb200_basket(mcb200_ctx *ctx, int precision, const mcb200_basket_t *opt, uint64_t n_paths, uint64_t seed,
+                  mcb200_result_t *out)
+{
+    return mcb200_basket_multi(&ctx, 1, precision, opt, n_paths, seed, out);
+}
+
+int mcb200_cva(mcb200_ctx *ctx, int precision, const mcb200_cva_t *cva, uint64_t n_paths, uint64_t seed,
+               mcb200_result_t *out)
+{
+    return mcb200_cva_multi(&ctx, 1, precision, cva, n_paths, seed, out);
+}
+
+// ---- per-path values ----
+int mcb200_vanilla_paths(mcb200_ctx *ctx, int precision, const mcb200_option_t *opt, uint64_t seed,
+                         uint64_t first_path, uint64_t n_paths, void *out_host)
+{
+    mcb200_plan_t plan;
+    int st = mcb200_plan_vanilla(precision, opt, first_path + n_paths, &plan);
+    if (st != MCB200_OK)
+        return st;
+    AnyJob job;
+    st = make_vanilla_job(precision, opt, seed, &job.vanilla);
+    if (st != MCB200_OK)
+        return st;
+    return paths(ctx, plan, job, first_path, n_paths, out_host);
+}
+
+int mcb200_basket_paths(mcb200_ctx *ctx, int precision, const mcb200_basket_t *opt, uint64_t seed,
+                        uint64_t first_path, uint64_t n_paths, void *out_host)
+{
+    mcb200_plan_t plan;
+    int st = mcb200_plan_basket(precision, opt, first_path + n_paths, &plan);
+    if (st != MCB200_OK)
+        return st;
+    AnyJob job;
+    st = make_basket_job(opt, seed, &job.basket);
+    if (st != MCB200_OK)
+        return st;
+    return paths(ctx, plan, job, first_path, n_paths, out_host);
+}
+
+int mcb200_cva_paths(mcb200_ctx *ctx, int precision, const mcb200_cva_t *cva, uint64_t seed, uint64_t first_path,
+                     uint64_t n_paths, void *out_host)
+{
+    mcb200_plan_t plan;
+    int st = mcb200_plan_cva(precision, cva, first_path + n_paths, &plan);
+    if (st != MCB200_OK)
+        return st;
+    AnyJob job;
+    st = make_cva_job(precision, cva, seed, &job.cva);
+    if (st != MCB200_OK)
+        return st;
+    return paths(ctx, plan, job, first_path, n_paths, out_host);
+}
+
+// ---- generator / reduction instrumentation ----
+int mcb200_debug_philox(mcb200_ctx *ctx, uint64_t n, const uint32_t *ctr_host, const uint32_t key[2],
+                        uint32_t *out_host)
+{
+    if (!ctx || !ctr_host || !key || !out_host || n == 0)
+        return MCB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    uint32_t *d_ctr = nullptr, *d_out = nullptr;
+    MCB_CUDA(ctx, cudaMalloc(&d_ctr, n * 16));
+    cudaError_t e = cudaMalloc(&d_out, n * 16);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_ctr, ctr_host, n * 16, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = debug_philox(n, d_ctr, make_keys((uint64_t)key[0] | ((uint64_t)key[1] << 32)), d_out, ctx->stream);
+    if (e == cudaSuccess) {
+        ctx->launches++;
+        e = cudaMemcpyAsync(out_host, d_out, n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ctr);
+    cudaFree(d_out);
+    if (e != cudaSuccess)
+        return fail_cuda(ctx, e, "debug_philox");
+    return MCB200_OK;
+}
+
+int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint32_t *ctr_host,
+                         const uint32_t key[2], void *out_host)
+{
+    if (!ctx || !ctr_host || !key || !out_host || n == 0 || (precision != MCB200_F32 && precision != MCB200_F64))
+        return MCB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    uint32_t *d_ctr = nullptr;
+    void *d_out = nullptr;
+    MCB_CUDA(ctx, cudaMalloc(&d_ctr, n * 16));
+    cudaError_t e = cudaMalloc(&d_out, n * 16);  // 4 floats or 2 doubles per counter
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_ctr, ctr_host, n * 16, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = debug_normals(precision, n, d_ctr, make_keys((uint64_t)key[0] | ((uint64_t)key[1] << 32)), d_out,
+                          ctx->stream);
+    if (e == cudaSuccess) {
+        ctx->launches++;
+        e = cudaMemcpyAsync(out_host, d_out, n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ctr);
+    cudaFree(d_out);
+    if (e != cudaSuccess)
+        return fail_cuda(ctx, e, "debug_normals");
+    return MCB200_OK;
+}
+
+int mcb200_debug_reduce(mcb200_ctx *ctx, const double *values_host, uint64_t n_valid, int unit_paths, int rounds,
+                        int accumulate_in_float, int scale_exp_sum, int scale_exp_sumsq,
+                        uint64_t acc_host[MCB200_ACC_WORDS])
+{
+    if (!ctx || !values_host || !acc_host || unit_paths < 1 || rounds < 1 || rounds > 64 ||
+        n_valid > (uint64_t)kThreads * rounds * unit_paths)
+        return MCB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    double *d_values = nullptr;
+    const size_t bytes = (size_t)(n_valid > 0 ? n_valid : 1) * sizeof(double);
+    MCB_CUDA(ctx, cudaMalloc(&d_values, bytes));
+    cudaError_t e = cudaMemcpyAsync(d_values, values_host, n_valid * sizeof(double), cudaMemcpyHostToDevice,
+                                    ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(ctx->d_acc, 0, sizeof(unsigned long long) * kAccWords, ctx->stream);
+    if (e == cudaSuccess)
+        e = debug_reduce(d_values, n_valid, unit_paths, rounds, accumulate_in_float != 0, scale_exp_sum,
+                         scale_exp_sumsq, ctx->d_acc, ctx->stream);
+    if (e == cudaSuccess) {
+        ctx->launches++;
+        e = cudaMemcpyAsync(ctx->h_acc, ctx->d_acc, sizeof(unsigned long long) * kAccWords, cudaMemcpyDeviceToHost,
+                            ctx->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_values);
+    if (e != cudaSuccess)
+        return fail_cuda(ctx, e, "debug_reduce");
+    std::memcpy(acc_host, ctx->h_acc, sizeof(uint64_t) * MCB200_ACC_WORDS);
+    return MCB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+// kernels_cva.cu -- CVA of one European call under Black-Scholes, fp32 and fp64 (sm_100a).
+//
+// Replaces geomBrownian + cnd + device_bsCall + cvaCallOptMC (DP/MonteCarloKernel.cu:104-129,
+// :222-283).  One draw unit = one path; exposure date j uses normal j of the path's sub-stream.
+// The state is the log-moneyness y = ln(S/K).  Per kept date j (host-built table, engine.cu):
+//   y  += mu_dt + sig_dt z                      exact GBM step
+//   s   = K e^y
+//   d1  = y inv_j + c1_j,  d2 = d1 - sig_j      inv_j = 1/(v sqrt(tau_j)), c1_j = (r + v^2/2) tau_j inv_j
+//   phi(d2) = phi(d1) s / kd_j                  kd_j = K e^{-r tau_j}: no second exponential
+//   ee  = s cnd(d1) - kd_j cnd(d2)              Hastings cnd, like the reference
+//   cva += w_j ee                               w_j = LGD (e^{-lambda t_{j-1}} - e^{-lambda t_j})
+// so a path-step costs one normal, two exponentials and two reciprocals; the reference spends six
+// exponentials, a log, three square roots and four divisions on it.  Dates the reference drops
+// (remaining time rounded below zero) are simply absent from the table.
+#include <vector>
+
+#include "device_math.cuh"
+#include "launch.h"
+#include "table_lock.h"
+
+namespace mcb {
+
+template <typename Real>
+struct CvaDate {
+    Real w, inv, c1, sig, kd, rkd;
+};
+
+constexpr int kCvaMaxDates = 1024;
+__constant__ __align__(16) unsigned char c_cva_table[kCvaMaxDates * sizeof(CvaDate<double>)];
+static TableLock g_cva_lock;
+
+template <typename Real> struct NormalsPerBlock;
+template <> struct NormalsPerBlock<float> { static constexpr int value = 4; };
+template <> struct NormalsPerBlock<double> { static constexpr int value = 2; };
+
+// pdf * polynomial(k), k = 1 / (1 + 0.2316419 |d|): the upper-tail probability of |d|
+// (Abramowitz-Stegun 26.2.17, the constants of DP/MonteCarloKernel.cu:111-116)
+template <typename Real>
+__device__ __forceinline__ Real hastings_tail(Real d, Real pdf)
+{
+    const Real k = rcp_real(fma((Real)0.2316419, fabs(d), (Real)1.0));
+    Real poly = fma(k, (Real)1.330274429, (Real)-1.821255978);
+    poly = fma(k, poly, (Real)1.781477937);
+    poly = fma(k, poly, (Real)-0.356563782);
+    poly = fma(k, poly, (Real)0.31938153);
+    return pdf * (k * poly);
+}
+
+template <typename RealT>
+struct Cva {
+    using Real = RealT;
+    static constexpr int kUnitPaths = 1;
+    static constexpr int kMinBlocks = 3;
+    static constexpr int kNpb = NormalsPerBlock<Real>::value;
+    struct Params {
+        PhiloxKeys keys;
+        Real y0, mu_dt, sig_dt, k;
+        int n_dates;  // kept dates
+    };
+    static __device__ __forceinline__ void step(const Params &P, const CvaDate<Real> &D, Real z, Real &y,
+                                                Real &cva)
+    {
+        y = fma(P.sig_dt, z, y + P.mu_dt);
+        const Real s = P.k * exp_real(y);
+        const Real d1 = fma(y, D.inv, D.c1);
+        const Real d2 = d1 - D.sig;
+        const Real pdf1 = (Real)0.39894228040143267793994605993438 * exp_real((Real)-0.5 * d1 * d1);
+        const Real pdf2 = pdf1 * s * D.rkd;
+        const Real t1 = hastings_tail(d1, pdf1);
+        const Real t2 = hastings_tail(d2, pdf2);
+        const Real n1 = d1 > 0 ? (Real)1.0 - t1 : t1;
+        const Real n2 = d2 > 0 ? (Real)1.0 - t2 : t2;
+        const Real ee = s * n1 - D.kd * n2;
+        cva = fma(D.w, ee, cva);
+    }
+    static __device__ __forceinline__ void eval(const Params &P, unsigned long long path, Real (&v)[1])
+    {
+        const CvaDate<Real> *dates = reinterpret_cast<const CvaDate<Real> *>(c_cva_table);
+        Real y = P.y0, cva = 0;
+#pragma unroll 1
+        for (int jb = 0; jb * kNpb < P.n_dates; jb++) {
+            uint32_t w[4];
+            philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)jb, kTagCva, P.keys, w);
+            Real z[kNpb];
+            normals_from_words(w, z);
+#pragma unroll
+            for (int q = 0; q < kNpb; q++) {
+                const int j = jb * kNpb + q;
+                if (j < P.n_dates)
+                    step(P, dates[j], z[q], y, cva);
+            }
+        }
+        v[0] = cva;
+    }
+};
+
+template <typename Real>
+static typename Cva<Real>::Params narrow(const CvaJob &job)
+{
+    typename Cva<Real>::Params p;
+    p.keys = job.keys;
+    p.y0 = (Real)job.y0;
+    p.mu_dt = (Real)job.mu_dt;
+    p.sig_dt = (Real)job.sig_dt;
+    p.k = (Real)job.k;
+    p.n_dates = job.n_dates;
+    return p;
+}
+
+template <typename Real>
+static cudaError_t launch_t(const CvaJob &job, const Geometry *geom, int grid, unsigned long long *d_acc,
+                            unsigned long long first_unit, unsigned long long n_units, void *d_out,
+                            cudaStream_t stream)
+{
+    if (job.n_dates < 0 || job.n_dates > kCvaMaxDates)
+        return cudaErrorInvalidValue;
+    std::vector<CvaDate<Real>> staging((size_t)(job.n_dates > 0 ? job.n_dates : 1));
+    for (int j = 0; j < job.n_dates; j++) {
+        const CvaDateHost &h = job.dates[j];
+        staging[j] = CvaDate<Real>{(Real)h.w, (Real)h.inv, (Real)h.c1, (Real)h.sig, (Real)h.kd, (Real)h.rkd};
+    }
+    TableUse use(g_cva_lock, stream);
+    if (use.status() != cudaSuccess)
+        return use.status();
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_cva_table, staging.data(), staging.size() * sizeof(CvaDate<Real>), 0,
+                                            cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess)
+        return e;
+    if (geom) {
+        mc_accumulate_kernel<Cva<Real>><<<grid, kThreads, 0, stream>>>(narrow<Real>(job), *geom, d_acc);
+    } else {
+        const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
+        mc_paths_kernel<Cva<Real>><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(
+            narrow<Real>(job), first_unit, n_units, (Real *)d_out);
+    }
+    return cudaGetLastError();
+}
+
+int cva_blocks_per_sm(int precision)
+{
+    int n = 0;
+    cudaError_t e = precision ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                    &n, mc_accumulate_kernel<Cva<double>>, kThreads, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                    &n, mc_accumulate_kernel<Cva<float>>, kThreads, 0);
+    return e == cudaSuccess ? n : 0;
+}
+
+cudaError_t cva_launch(int precision, const CvaJob &job, const Geometry &geom, int grid,
+                       unsigned long long *d_acc, cudaStream_t stream)
+{
+    return precision ? launch_t<double>(job, &geom, grid, d_acc, 0, 0, nullptr, stream)
+                     : launch_t<float>(job, &geom, grid, d_acc, 0, 0, nullptr, stream);
+}
+
+cudaError_t cva_paths(int precision, const CvaJob &job, unsigned long long first_unit,
+                      unsigned long long n_units, void *d_out, cudaStream_t stream)
+{
+    return precision ? launch_t<double>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream)
+                     : launch_t<float>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream);
+}
+
+}  // namespace mcb

@@ -1,0 +1,114 @@
+// kernels_debug.cu -- parity instrumentation: the generator, the normal transform and the chunk
+// reduction exposed on their own, running the SAME device functions as the pricing kernels, so the
+// tests can compare them bit for bit (integer stages) or within a stated tolerance (normals) with
+// the CPU oracle.
+#include "device_math.cuh"
+#include "launch.h"
+
+namespace mcb {
+
+__global__ void debug_philox_kernel(unsigned long long n, const uint32_t *__restrict__ ctr,
+                                    const __grid_constant__ PhiloxKeys keys, uint32_t *__restrict__ out)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t w[4];
+        philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], keys, w);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            out[4 * i + q] = w[q];
+    }
+}
+
+template <typename Real, int kPerBlock>
+__global__ void debug_normals_kernel(unsigned long long n, const uint32_t *__restrict__ ctr,
+                                     const __grid_constant__ PhiloxKeys keys, Real *__restrict__ out)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t w[4];
+        philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], keys, w);
+        Real z[kPerBlock];
+        normals_from_words(w, z);
+#pragma unroll
+        for (int q = 0; q < kPerBlock; q++)
+            out[kPerBlock * i + q] = z[q];
+    }
+}
+
+// One chunk of given per-path values through the pricing kernels' accumulation order and
+// chunk_commit / scratch_flush.
+__global__ void __launch_bounds__(kThreads)
+debug_reduce_kernel(const double *__restrict__ values, unsigned long long n_valid, int unit_paths,
+                    bool accumulate_in_float, const __grid_constant__ Geometry G,
+                    unsigned long long *__restrict__ acc)
+{
+    __shared__ BlockScratch sc;
+    scratch_init(sc);
+    double s = 0, s2 = 0;
+    float fs = 0, fs2 = 0;
+    for (int k = 0; k < G.rounds; k++) {
+        const unsigned long long unit = (unsigned long long)k * kThreads + threadIdx.x;
+        for (int q = 0; q < unit_paths; q++) {
+            const unsigned long long idx = unit * (unsigned long long)unit_paths + q;
+            if (idx >= n_valid)
+                continue;
+            if (accumulate_in_float) {
+                const float x = (float)values[idx];
+                fs += x;
+                fs2 = fmaf(x, x, fs2);
+            } else {
+                const double x = values[idx];
+                s += x;
+                s2 = fma(x, x, s2);
+            }
+        }
+    }
+    if (accumulate_in_float) {
+        s = (double)fs;
+        s2 = (double)fs2;
+    }
+    chunk_commit(s, s2, n_valid, G, sc);
+    scratch_flush(sc, acc);
+}
+
+static int grid_for(unsigned long long n)
+{
+    const unsigned long long blocks = (n + kThreads - 1) / kThreads;
+    return (int)(blocks < 1 ? 1 : (blocks < 65535ull ? blocks : 65535ull));
+}
+
+cudaError_t debug_philox(unsigned long long n, const uint32_t *d_ctr, PhiloxKeys keys, uint32_t *d_out,
+                         cudaStream_t stream)
+{
+    debug_philox_kernel<<<grid_for(n), kThreads, 0, stream>>>(n, d_ctr, keys, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t debug_normals(int precision, unsigned long long n, const uint32_t *d_ctr, PhiloxKeys keys,
+                          void *d_out, cudaStream_t stream)
+{
+    if (precision)
+        debug_normals_kernel<double, 2><<<grid_for(n), kThreads, 0, stream>>>(n, d_ctr, keys, (double *)d_out);
+    else
+        debug_normals_kernel<float, 4><<<grid_for(n), kThreads, 0, stream>>>(n, d_ctr, keys, (float *)d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t debug_reduce(const double *d_values, unsigned long long n_valid, int unit_paths, int rounds,
+                         bool accumulate_in_float, int scale_exp_sum, int scale_exp_sumsq,
+                         unsigned long long *d_acc, cudaStream_t stream)
+{
+    Geometry g{};
+    g.total_paths = n_valid;
+    g.chunk_units = (unsigned long long)kThreads * rounds;
+    g.first_chunk = 0;
+    g.n_chunks = 1;
+    g.rounds = rounds;
+    g.scale_exp_sum = scale_exp_sum;
+    g.scale_exp_sumsq = scale_exp_sumsq;
+    debug_reduce_kernel<<<1, kThreads, 0, stream>>>(d_values, n_valid, unit_paths, accumulate_in_float, g, d_acc);
+    return cudaGetLastError();
+}
+
+}  // namespace mcb

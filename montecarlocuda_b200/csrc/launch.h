@@ -1,0 +1,67 @@
+// launch.h -- host-callable launchers of the pricing kernels (one translation unit per workload,
+// each owning its __constant__ table).  Internal to libmcb200; the public ABI is include/mcb200.h.
+#pragma once
+
+#include "device_common.cuh"
+
+namespace mcb {
+
+enum : uint32_t { kTagVanilla = 1u, kTagBasket = 2u, kTagCva = 3u };
+
+// ---- vanilla (DP/MonteCarloKernel.cu:67-71, :179-220) ----
+// a, b in log2 units for fp32 and natural-log units for fp64 (see kernels_vanilla.cu)
+struct VanillaJob {
+    PhiloxKeys keys;
+    double a, b, k;
+};
+int vanilla_blocks_per_sm(int precision);
+cudaError_t vanilla_launch(int precision, const VanillaJob &job, const Geometry &geom, int grid,
+                           unsigned long long *d_acc, cudaStream_t stream);
+cudaError_t vanilla_paths(int precision, const VanillaJob &job, unsigned long long first_unit,
+                          unsigned long long n_units, void *d_out, cudaStream_t stream);
+
+// ---- basket (DP/MonteCarloKernel.cu:74-101, :133-177) ----
+// all arrays in natural-log units and fp64; the launcher narrows / rescales for the kernel
+struct BasketJob {
+    PhiloxKeys keys;
+    int n;                 // assets
+    bool full;             // factor has entries above the diagonal
+    const double *factor;  // row-major n x n, already scaled: v_i sqrt(T) L_ij
+    const double *a;       // (r - v_i^2/2) T + v_i sqrt(T) d_i
+    const double *m;       // w_i s_i
+    double k;
+};
+int basket_padded_width(int n);  // template width that serves n assets, 0 if unsupported
+int basket_blocks_per_sm(int precision, int n, bool full);
+cudaError_t basket_launch(int precision, const BasketJob &job, const Geometry &geom, int grid,
+                          unsigned long long *d_acc, cudaStream_t stream);
+cudaError_t basket_paths(int precision, const BasketJob &job, unsigned long long first_unit,
+                         unsigned long long n_units, void *d_out, cudaStream_t stream);
+
+// ---- CVA (DP/MonteCarloKernel.cu:104-129, :222-283) ----
+struct CvaDateHost {
+    double w, inv, c1, sig, kd, rkd;
+};
+struct CvaJob {
+    PhiloxKeys keys;
+    double y0, mu_dt, sig_dt, k;
+    int n_dates;               // kept dates
+    const CvaDateHost *dates;  // n_dates entries
+};
+int cva_blocks_per_sm(int precision);
+cudaError_t cva_launch(int precision, const CvaJob &job, const Geometry &geom, int grid,
+                       unsigned long long *d_acc, cudaStream_t stream);
+cudaError_t cva_paths(int precision, const CvaJob &job, unsigned long long first_unit,
+                      unsigned long long n_units, void *d_out, cudaStream_t stream);
+
+// ---- instrumentation (kernels_debug.cu) ----
+cudaError_t debug_philox(unsigned long long n, const uint32_t *d_ctr, PhiloxKeys keys, uint32_t *d_out,
+                         cudaStream_t stream);
+cudaError_t debug_normals(int precision, unsigned long long n, const uint32_t *d_ctr, PhiloxKeys keys,
+                          void *d_out, cudaStream_t stream);
+cudaError_t debug_reduce(const double *d_values, unsigned long long n_valid, int unit_paths, int rounds,
+                         bool accumulate_in_float, int scale_exp_sum, int scale_exp_sumsq,
+                         unsigned long long *d_acc, cudaStream_t stream);
+
+
+}  // namespace mcb

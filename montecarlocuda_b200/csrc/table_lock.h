@@ -1,0 +1,52 @@
+// table_lock.h -- a __constant__ table is per device and shared by every stream and context of
+// the process, so its users are serialised: the upload of the next job waits (on the device, via
+// an event) for the kernel of the previous one, and the host-side sequence upload -> launch ->
+// record is atomic under a mutex.  The reference has the same hazard (file-scope __constant__
+// OPTION / MOPTION, DP/MonteCarloKernel.cu:53-59) and no protection.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <mutex>
+
+namespace mcb {
+
+struct TableLock {
+    static constexpr int kMaxDevices = 64;
+    std::mutex mu;
+    cudaEvent_t last_use[kMaxDevices] = {};
+    bool used[kMaxDevices] = {};
+};
+
+class TableUse {
+public:
+    TableUse(TableLock &lock, cudaStream_t stream) : lock_(lock), stream_(stream)
+    {
+        lock_.mu.lock();
+        status_ = cudaGetDevice(&device_);
+        if (status_ == cudaSuccess && (device_ < 0 || device_ >= TableLock::kMaxDevices))
+            status_ = cudaErrorInvalidDevice;
+        if (status_ == cudaSuccess && lock_.used[device_])
+            status_ = cudaStreamWaitEvent(stream_, lock_.last_use[device_], 0);
+    }
+    ~TableUse()
+    {
+        if (status_ == cudaSuccess) {
+            if (!lock_.used[device_]) {
+                if (cudaEventCreateWithFlags(&lock_.last_use[device_], cudaEventDisableTiming) == cudaSuccess)
+                    lock_.used[device_] = true;
+            }
+            if (lock_.used[device_])
+                cudaEventRecord(lock_.last_use[device_], stream_);
+        }
+        lock_.mu.unlock();
+    }
+    cudaError_t status() const { return status_; }
+
+private:
+    TableLock &lock_;
+    cudaStream_t stream_;
+    int device_ = -1;
+    cudaError_t status_ = cudaSuccess;
+};
+
+}  // namespace mcb

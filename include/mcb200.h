@@ -130,7 +130,7 @@ int mcb200_cva_multi(mcb200_ctx **ctxs, int n_ctx, int precision, const mcb200_c
 /* ---- sharded pricing (one process per GPU; the combine is the caller's all-reduce) ----
  * plan -> shard range for (rank, world) -> asynchronous launch accumulating into a DEVICE
  * accumulator block (MCB200_ACC_WORDS zero-initialised 64-bit words owned by the caller) on the
- * given stream (a cudaStream_t passed as void*, NULL = the context's own stream) ->
+ * given stream (a cudaStream_t passed as void*; NULL is CUDA's default stream, as everywhere) ->
  * [int64 SUM all-reduce of the block] -> mcb200_finalize on a host copy. */
 int mcb200_plan_vanilla(int precision, const mcb200_option_t *opt, uint64_t n_paths, mcb200_plan_t *plan);
 int mcb200_plan_basket(int precision, const mcb200_basket_t *opt, uint64_t n_paths, mcb200_plan_t *plan);

@@ -632,7 +632,7 @@ int mcb200_vanilla_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb2
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
     return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
-                   stream ? (cudaStream_t)stream : ctx->stream);
+                   (cudaStream_t)stream);
 }
 
 int mcb200_basket_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_basket_t *opt, uint64_t seed,
@@ -651,7 +651,7 @@ int mcb200_basket_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb20
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
     return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
-                   stream ? (cudaStream_t)stream : ctx->stream);
+                   (cudaStream_t)stream);
 }
 
 int mcb200_cva_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_cva_t *cva, uint64_t seed,
@@ -670,7 +670,7 @@ int mcb200_cva_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_c
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
     return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
-                   stream ? (cudaStream_t)stream : ctx->stream);
+                   (cudaStream_t)stream);
 }
 
 // ---- one-call pricing ----

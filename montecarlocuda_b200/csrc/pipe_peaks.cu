@@ -171,8 +171,14 @@ int measure(const char *name, int sms, typename Op::T a, typename Op::T b, bool 
     const double per_thread = (double)iters * kInner * kChains;
     const double per_sm = per_thread * threads * 2;
     const double total = per_thread * threads * blocks;
-    std::printf("  \"%s\": {\"per_clk_per_sm\": %.2f, \"gops\": %.1f, \"ms\": %.4f, \"sm_mhz_effective\": %.0f}%s\n", name,
-                per_sm / mean_cycles, total / (best_ms * 1e6), best_ms, mean_cycles / (best_ms * 1e3), last ? "" : ",");
+    // clock64() does not tick at the SM clock on this platform (it reads ~1461 MHz while FFMA
+    // retires 124/clk/SM at clocks.max.sm), so the per-clock figure is also given at clocks.max.sm
+    cudaDeviceProp prop;
+    CHECK(cudaGetDeviceProperties(&prop, 0));
+    const double gops = total / (best_ms * 1e6);
+    std::printf("  \"%s\": {\"gops\": %.1f, \"per_clk_per_sm_at_max_clock\": %.2f, \"per_clock64_tick_per_sm\": %.2f, \"ms\": %.4f, "
+                "\"clock64_mhz\": %.0f}%s\n", name, gops, gops * 1e9 / ((double)sms * prop.clockRate * 1e3),
+                per_sm / mean_cycles, best_ms, mean_cycles / (best_ms * 1e3), last ? "" : ",");
     cudaFree(d_out);
     cudaFree(d_cycles);
     cudaEventDestroy(e0);

@@ -166,6 +166,10 @@ int mcb200_debug_philox(mcb200_ctx *ctx, uint64_t n, const uint32_t *ctr_host, c
                         uint32_t *out_host);
 int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint32_t *ctr_host,
                          const uint32_t key[2], void *out_host);
+/* the hand-built fp64 special functions of the kernels, element-wise on n host doubles:
+ * fn 0 = -2 ln(u), 1 = sqrt, 2 = 1/x, 3 = e^x, 4 = cos and sin of 2 pi k / 2^52 (the input's bit
+ * pattern is the 52-bit integer k).  out_host receives 2 doubles per element (second = sin for fn 4). */
+int mcb200_debug_math64(mcb200_ctx *ctx, int fn, uint64_t n, const double *in_host, double *out_host);
 /* reduce ONE chunk of given per-path values with the pricing kernels' block reduction and
  * integer split; acc_host receives the accumulator block */
 int mcb200_debug_reduce(mcb200_ctx *ctx, const double *values_host, uint64_t n_valid, int unit_paths,

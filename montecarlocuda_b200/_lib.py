@@ -81,6 +81,7 @@ _SIGNATURES = {
     "mcb200_cva_paths": (C.c_int, [_CTX, C.c_int, _P(CvaT), C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mcb200_debug_philox": (C.c_int, [_CTX, C.c_uint64, C.c_void_p, _P(C.c_uint32), C.c_void_p]),
     "mcb200_debug_normals": (C.c_int, [_CTX, C.c_int, C.c_uint64, C.c_void_p, _P(C.c_uint32), C.c_void_p]),
+    "mcb200_debug_math64": (C.c_int, [_CTX, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mcb200_debug_reduce": (C.c_int, [_CTX, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 

@@ -186,6 +186,13 @@ class Engine:
         _lib.check(self._lib.mcb200_debug_normals(self._ctx, p, len(ctr), ctr.ctypes.data, k, out.ctypes.data), self._ctx)
         return out
 
+    def math64(self, fn: int, x: np.ndarray) -> np.ndarray:
+        """The kernels' fp64 special functions on an array (fn: 0 -2ln u, 1 sqrt, 2 1/x, 3 e^x, 4 cos/sin turn)."""
+        v = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty((len(v), 2), dtype=np.float64)
+        _lib.check(self._lib.mcb200_debug_math64(self._ctx, int(fn), len(v), v.ctypes.data, out.ctypes.data), self._ctx)
+        return out
+
     def reduce_chunk(self, values: np.ndarray, unit_paths: int, rounds: int, accumulate_in_float: bool,
                      scale_exp_sum: int, scale_exp_sumsq: int) -> np.ndarray:
         v = np.ascontiguousarray(values, dtype=np.float64)

@@ -138,7 +138,9 @@ __device__ __forceinline__ void scratch_flush(const BlockScratch &sc, unsigned l
 //   W::Real            float or double: the per-path arithmetic type
 //   W::Params          by-value parameter block (constant bank)
 //   W::kUnitPaths      paths served by one draw unit
-//   W::eval(P, unit, v) fills v[kUnitPaths] with the per-path values of draw unit `unit`
+//   W::kMinBlocks      CTAs per SM the register budget is sized for; W::kUnroll  unroll of the unit loop
+//   W::Shared          per-CTA shared-memory state (the fp64 math tables; empty for fp32)
+//   W::eval(P, unit, v, sh) fills v[kUnitPaths] with the per-path values of draw unit `unit`
 // A CTA walks chunks first_chunk + blockIdx.x, + gridDim.x, ...; thread t of a chunk owns units
 // base + k * 256 + t for k < rounds, in that order, and accumulates value and value^2 in W::Real
 // (short runs: at most rounds * kUnitPaths <= 256 terms) before the fp64 block reduction.
@@ -149,6 +151,8 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
 {
     using Real = typename W::Real;
     __shared__ BlockScratch sc;
+    __shared__ typename W::Shared sh;
+    sh.load();
     scratch_init(sc);
     const unsigned long long last = G.first_chunk + G.n_chunks;
     for (unsigned long long chunk = G.first_chunk + blockIdx.x; chunk < last; chunk += gridDim.x) {
@@ -166,13 +170,13 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
         if (whole || W::kUnitPaths == 1) {
             // one path per unit: the same loop serves the job's last (partial) chunk, so the
             // (large) estimator body is instantiated once
-#pragma unroll 1
+#pragma unroll W::kUnroll
             for (int k = 0; k < G.rounds; k++) {
                 const unsigned long long unit = base + (unsigned long long)k * kThreads + threadIdx.x;
                 if (W::kUnitPaths == 1 && !whole && unit >= G.total_paths)
                     break;
                 Real v[W::kUnitPaths];
-                W::eval(P, unit, v);
+                W::eval(P, unit, v, sh);
 #pragma unroll
                 for (int q = 0; q < W::kUnitPaths; q++) {
                     s += v[q];
@@ -187,7 +191,7 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
                 if (unit * (unsigned long long)W::kUnitPaths >= G.total_paths)
                     break;
                 Real v[W::kUnitPaths];
-                W::eval(P, unit, v);
+                W::eval(P, unit, v, sh);
 #pragma unroll
                 for (int q = 0; q < W::kUnitPaths; q++) {
                     if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths) {
@@ -208,10 +212,13 @@ __global__ void __launch_bounds__(kThreads)
 mc_paths_kernel(const __grid_constant__ typename W::Params P, unsigned long long first_unit,
                 unsigned long long n_units, typename W::Real *__restrict__ out)
 {
+    __shared__ typename W::Shared sh;
+    sh.load();
+    __syncthreads();
     for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n_units;
          i += (unsigned long long)gridDim.x * kThreads) {
         typename W::Real v[W::kUnitPaths];
-        W::eval(P, first_unit + i, v);
+        W::eval(P, first_unit + i, v, sh);
 #pragma unroll
         for (int q = 0; q < W::kUnitPaths; q++)
             out[i * W::kUnitPaths + q] = v[q];

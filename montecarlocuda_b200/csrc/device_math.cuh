@@ -9,7 +9,30 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "device_math64.cuh"
+
 namespace mcb {
+
+// Per-CTA shared-memory state of a workload: nothing for fp32 (every special function is a MUFU
+// op), the log / exp tables for fp64.  load() is called by all threads of the CTA before the
+// first barrier of the kernel.
+struct NoShared {
+    __device__ __forceinline__ void load() {}
+};
+struct SharedTables64 {
+    Tables64 t;
+    __device__ __forceinline__ void load()
+    {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            t.log_tab[i][0] = kLogTable[i][0];
+            t.log_tab[i][1] = kLogTable[i][1];
+            t.exp_tab[i] = kExpTable[i];
+        }
+    }
+};
+template <typename Real> struct SharedFor;
+template <> struct SharedFor<float> { using type = NoShared; };
+template <> struct SharedFor<double> { using type = SharedTables64; };
 
 // ---- fp32: every transcendental is ONE MUFU op (no denormal fix-up, no range-reduction code) ----
 __device__ __forceinline__ float mufu_lg2(float x)
@@ -67,7 +90,7 @@ __device__ __forceinline__ void box_muller_f32(uint32_t wa, uint32_t wb, float &
     z1 = r * mufu_sin(a);
 }
 
-__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float (&z)[4])
+__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float (&z)[4], const NoShared &)
 {
     box_muller_f32(w[0], w[1], z[0], z[1]);
     box_muller_f32(w[2], w[3], z[2], z[3]);
@@ -81,22 +104,27 @@ __device__ __forceinline__ double stuffed_unit_f64(uint32_t w_hi, uint32_t w_lo)
 }
 
 // Four words -> one fp64 Box-Muller pair (true 52-bit uniforms; the reference's "double" normals
-// are float).
-__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], double (&z)[2])
+// are float): radius from (w0, w1), angle k / 2^52 turns from (w2, w3).
+// 9 + 7 + 18 + 3 = 37 fp64 instructions per pair on the hand-built functions of device_math64.cuh
+// (libdevice log + sqrt + sincospi: 68).
+__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], double (&z)[2], const SharedTables64 &sh)
 {
     const double u = 2.0 - stuffed_unit_f64(w[0], w[1]);
-    const double r = sqrt(-2.0 * log(u));
-    const double t = stuffed_unit_f64(w[2], w[3]) - 1.0;  // turn fraction in [0, 1)
-    double sn, cs;
-    sincospi(2.0 * t, &sn, &cs);
+    const double r = sqrt_pos(fabs(neg2log_unit(u, sh.t)));
+    double cs, sn;
+    sincos_turn(w[2], w[3], cs, sn);
     z[0] = r * cs;
     z[1] = r * sn;
 }
 
+// max(x, 0): FMNMX for fp32; for fp64 an integer mask (fmax(double) is DSETP + selects + NaN fix-up)
+__device__ __forceinline__ float positive_part(float x) { return fmaxf(x, 0.0f); }
+__device__ __forceinline__ double positive_part(double x) { return relu64(x); }
+
 // precision-generic wrappers used by the workload policies
-__device__ __forceinline__ float exp_real(float x) { return mufu_ex2(x * 1.4426950408889634f); }
-__device__ __forceinline__ double exp_real(double x) { return exp(x); }
+__device__ __forceinline__ float exp_real(float x, const NoShared &) { return mufu_ex2(x * 1.4426950408889634f); }
+__device__ __forceinline__ double exp_real(double x, const SharedTables64 &sh) { return exp_tab(x, sh.t); }
 __device__ __forceinline__ float rcp_real(float x) { return mufu_rcp(x); }
-__device__ __forceinline__ double rcp_real(double x) { return 1.0 / x; }
+__device__ __forceinline__ double rcp_real(double x) { return rcp_newton(x); }
 
 }  // namespace mcb

@@ -1,0 +1,206 @@
+// device_math64.cuh -- the fp64 special functions of the pricing kernels, hand-built for the
+// sm_100a pipe mix: the fp64 pipe retires 64 thread-instr/clk/SM and there is no fp64 MUFU, so
+// libdevice's log / sincospi / exp / division cost 30 / 27 / 18 / 8+ fp64 instructions plus as many
+// integer ones (measured: 162 warp-instructions per vanilla path, profiles/r01a_*).  Here:
+//
+//   neg2log_unit   -2 ln(u), u in (0,1]   table of 256 reciprocals (shared memory) + degree-6 log1p   9 fp64
+//   sqrt_pos       sqrt(x)                MUFU.RSQ64H seed + 2 coupled Newton steps                   7 fp64
+//   sincos_turn    cos/sin(2 pi k/2^52)   octant taken from the integer bits (exact reduction),
+//                                         fdlibm kernel polynomials on [0, pi/4]                     18 fp64
+//   exp_tab        e^x                    n = rint(256 x / ln2) by magic add, Cody-Waite, table of
+//                                         2^(j/256), degree-4 expm1, exponent added as an integer     9 fp64
+//   rcp_newton     1/x                    MUFU.RCP64H seed + 2 Newton steps                           4 fp64
+//
+// Accuracy (checked on the CPU against libm by tests/test_device_math64.py through the host build
+// of this very header, and on the GPU against the oracle): <= 2 ulp for exp/sqrt/rcp/sincos,
+// <= 2.5e-16 absolute on -2 ln u.
+//
+// The header compiles both for the device and, with MCB_HOST_MATH defined, for the host (MUFU
+// seeds emulated at their documented precision), which is how the accuracy tests run without a GPU.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+
+#ifdef MCB_HOST_MATH
+#include <cmath>
+#define MCB_FN static inline
+#define MCB_TABLE static const
+#else
+#include <cuda_runtime.h>
+#define MCB_FN __device__ __forceinline__
+#define MCB_TABLE __device__ const
+#endif
+
+namespace mcb {
+#ifdef MCB_HOST_MATH
+namespace hostmath {
+#endif
+
+#include "tables64.inc"
+
+// ---- bit access and the two MUFU seeds -----------------------------------------------------------
+#ifdef MCB_HOST_MATH
+MCB_FN int hi_word(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+MCB_FN int lo_word(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (int)(uint32_t)b; }
+MCB_FN double make_double(int hi, int lo)
+{
+    uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x;
+    std::memcpy(&x, &b, 8);
+    return x;
+}
+MCB_FN double fma_(double a, double b, double c) { return std::fma(a, b, c); }
+// MUFU.RSQ64H / MUFU.RCP64H work on the high word and deliver ~2^-22 relative error (PTX ISA:
+// rsqrt.approx.ftz.f64, rcp.approx.ftz.f64); emulate by truncating the input to its high word
+// and the result to its high word (20 mantissa bits: a little worse than the hardware)
+MCB_FN double seed_trunc(double y) { return make_double(hi_word(y), 0); }
+MCB_FN double rsqrt_seed(double x) { return seed_trunc(1.0 / std::sqrt(make_double(hi_word(x), 0))); }
+MCB_FN double rcp_seed(double x) { return seed_trunc(1.0 / make_double(hi_word(x), 0)); }
+#else
+MCB_FN int hi_word(double x) { return __double2hiint(x); }
+MCB_FN int lo_word(double x) { return __double2loint(x); }
+MCB_FN double make_double(int hi, int lo) { return __hiloint2double(hi, lo); }
+MCB_FN double fma_(double a, double b, double c) { return fma(a, b, c); }
+MCB_FN double rsqrt_seed(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+MCB_FN double rcp_seed(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+#endif
+
+// The tables live in shared memory inside the kernels (random per-thread indices: a constant-bank
+// read would serialise); this is the view the functions take.
+struct Tables64 {
+    double log_tab[256][2];  // { c_i, -ln c_i }
+    double exp_tab[256];     // 2^(j/256)
+};
+
+// ---- -2 ln(u) for u in (0, 1] --------------------------------------------------------------------
+// u = 2^e m, m in [1,2); i = top 8 mantissa bits; r = m c_i - 1 in [0, 2^-8);
+// ln u = e ln2 + (-ln c_i) + log1p(r), log1p by its degree-6 Taylor polynomial (|error| < 2^-59).
+// The result can come out as -1e-17 instead of +0 when u is one ulp below 1; callers take |.|.
+MCB_FN double neg2log_unit(double u, const Tables64 &T)
+{
+    const int hi = hi_word(u);
+    const int idx = (hi >> 12) & 0xff;
+    const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(u));
+    // exponent as a double without a conversion instruction: 2^52 + biased exponent, minus (2^52 + 1023)
+    const double e = make_double(0x43300000, (int)((unsigned)hi >> 20)) - 4503599627371519.0;
+    const double c = T.log_tab[idx][0];
+    const double l = T.log_tab[idx][1];
+    const double r = fma_(m, c, -1.0);
+    double q = fma_(r, -1.0 / 6.0, 0.2);
+    q = fma_(r, q, -0.25);
+    q = fma_(r, q, 1.0 / 3.0);
+    q = fma_(r, q, -0.5);
+    const double p = fma_(r * r, q, r);                    // log1p(r)
+    // -2 (e ln2 + l) + 1e-300: the tiny offset (free: it rides in an FMA) keeps the result away from
+    // an exact 0 at u == 1, so the square root below needs no zero guard
+    const double t = fma_(e, -2.0 * 0x1.62e42fefa39efp-1, fma_(l, -2.0, 1e-300));
+    return fma_(p, -2.0, t);
+}
+
+// ---- sqrt(x), x > 0 finite and normal ------------------------------------------------------------
+// y ~ 1/sqrt(x) to 2^-22; g = x y, h = y/2; two coupled Newton steps r = 1/2 - h g; g += g r; h += h r.
+// No zero guard: the only caller feeds |neg2log_unit| >= 1e-300.
+MCB_FN double sqrt_pos(double x)
+{
+    const double y = rsqrt_seed(x);
+    double g = x * y;
+    double h = 0.5 * y;
+    double r = fma_(-h, g, 0.5);
+    g = fma_(g, r, g);
+    h = fma_(h, r, h);
+    r = fma_(-h, g, 0.5);
+    return fma_(g, r, g);
+}
+
+// ---- 1/x, x finite and not tiny ------------------------------------------------------------------
+MCB_FN double rcp_newton(double x)
+{
+    double y = rcp_seed(x);
+    double e = fma_(-x, y, 1.0);
+    y = fma_(y, e, y);
+    e = fma_(-x, y, 1.0);
+    return fma_(y, e, y);
+}
+
+// ---- cos and sin of 2 pi k / 2^52 for a 52-bit integer k = (k_hi[19:0] : k_lo) --------------------
+// octant q = top 3 bits, frac = the other 49 bits (exact); odd octants are reflected (1 - frac,
+// exact), phi = frac pi/4 in [0, pi/4]; fdlibm __kernel_sin / __kernel_cos polynomials; the
+// octant's swap and signs are integer selects / sign-bit XORs.
+MCB_FN void sincos_turn(uint32_t k_hi, uint32_t k_lo, double &cs, double &sn)
+{
+    const uint32_t q = (k_hi >> 17) & 7u;
+    // d in [1,2): 49 fraction bits moved up by 3
+    const uint32_t fh = ((k_hi << 3) | (k_lo >> 29)) & 0x000fffffu;
+    const double d = make_double((int)(fh | 0x3ff00000u), (int)(k_lo << 3));
+    const bool odd = (q & 1u) != 0u;
+    // y = odd ? 2 - d : d - 1   (exact): flip d's sign bit for odd octants, add 2 or -1
+    const double ds = make_double(hi_word(d) ^ (int)(odd ? 0x80000000u : 0u), lo_word(d));
+    const double y = ds + make_double(odd ? 0x40000000 : (int)0xbff00000u, 0);
+    const double x = y * 0x1.921fb54442d18p-1;  // pi/4
+    const double z = x * x;
+    double s = fma_(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    s = fma_(z, s, 2.75573137070700676789e-06);
+    s = fma_(z, s, -1.98412698298579493134e-04);
+    s = fma_(z, s, 8.33333333332248946124e-03);
+    s = fma_(z, s, -1.66666666666666324348e-01);
+    const double sin_phi = fma_(x * z, s, x);
+    double c = fma_(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    c = fma_(z, c, -2.75573143513906633035e-07);
+    c = fma_(z, c, 2.48015872894767294178e-05);
+    c = fma_(z, c, -1.38888888888741095749e-03);
+    c = fma_(z, c, 4.16666666666666019037e-02);
+    const double cos_phi = fma_(z * z, c, fma_(z, -0.5, 1.0));
+    // octant table: swap for q in {1,2,5,6}; cos negative for q in {2,3,4,5}; sin negative for q >= 4
+    const bool swap = ((q + 1u) & 2u) != 0u;
+    const double a = swap ? sin_phi : cos_phi;
+    const double b = swap ? cos_phi : sin_phi;
+    const int cos_sign = (int)(((q + 2u) & 4u) << 29);
+    const int sin_sign = (int)((q & 4u) << 29);
+    cs = make_double(hi_word(a) ^ cos_sign, lo_word(a));
+    sn = make_double(hi_word(b) ^ sin_sign, lo_word(b));
+}
+
+// ---- e^x -----------------------------------------------------------------------------------------
+// n = rint(x 256/ln2) (magic-number add), r = x - n ln2/256 (Cody-Waite, |r| <= ln2/512),
+// e^x = 2^(n>>8) * T[n & 255] * (1 + r + r^2/2 + r^3/6 + r^4/24).  The power of two is added to the
+// exponent field as an integer, so the argument must satisfy |x| <= 700: the host validates every
+// job's reachable exponent range (engine.cu: make_*_job) and the CVA kernel floors -d^2/2 at -700.
+MCB_FN double exp_tab(double x, const Tables64 &T)
+{
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    const double t = fma_(x, 0x1.71547652b82fep+8, magic);
+    const int n = lo_word(t);
+    const double nd = t - magic;
+    double r = fma_(nd, -0x1.62e42fee00000p-9, x);
+    r = fma_(nd, -0x1.a39ef35793c76p-41, r);
+    const double tj = T.exp_tab[n & 255];
+    double p = fma_(r, 1.0 / 24.0, 1.0 / 6.0);
+    p = fma_(r, p, 0.5);
+    p = fma_(r * r, p, r);          // e^r - 1
+    const double v = fma_(tj, p, tj);
+    return make_double(hi_word(v) + ((n >> 8) << 20), lo_word(v));
+}
+
+// ---- max(x, 0) on the integer pipe: clear every bit when the sign bit is set ----------------------
+MCB_FN double relu64(double x)
+{
+    const int hi = hi_word(x);
+    const int keep = ~(hi >> 31);
+    return make_double(hi & keep, lo_word(x) & keep);
+}
+
+#ifdef MCB_HOST_MATH
+}  // namespace hostmath
+#endif
+}  // namespace mcb

@@ -171,6 +171,9 @@ int make_vanilla_job(int precision, const mcb200_option_t *o, uint64_t seed, Van
     job->a = (std::log(o->s) + (o->r - 0.5 * o->v * o->v) * o->t) * unit;
     job->b = o->v * std::sqrt(o->t) * unit;
     job->k = o->k;
+    // the table-driven exponential takes |exponent| <= 700 in natural-log units (normals reach |z| < 8.6)
+    if (!(std::fabs(job->a) + 9.0 * std::fabs(job->b) < 700.0 * unit))
+        return MCB200_ERR_INVALID;
     return MCB200_OK;
 }
 
@@ -209,6 +212,11 @@ int make_basket_job(const mcb200_basket_t *o, uint64_t seed, BasketTables *t)
         }
         t->a[i] = (o->r - 0.5 * o->v[i] * o->v[i]) * o->t + o->v[i] * sqrt_t * o->d[i];
         t->m[i] = o->w[i] * o->s[i];
+        double reach = std::fabs(t->a[i]);
+        for (int j = 0; j < n; j++)
+            reach += 9.0 * std::fabs(t->factor[(size_t)i * n + j]);
+        if (!(reach < 700.0))  // range of the table-driven exponential
+            return MCB200_ERR_INVALID;
     }
     t->job.keys = make_keys(seed);
     t->job.n = n;
@@ -293,6 +301,8 @@ int make_cva_job(int precision, const mcb200_cva_t *c, uint64_t seed, CvaTables 
         }
         d.rkd = 1.0 / d.kd;
     }
+    if (!(std::fabs(std::log(o.s / o.k)) + n * (std::fabs((o.r - 0.5 * o.v * o.v) * dt) + 9.0 * o.v * std::sqrt(dt)) < 700.0))
+        return MCB200_ERR_INVALID;  // range of the table-driven exponential
     t->job.keys = make_keys(seed);
     t->job.y0 = std::log(o.s / o.k);
     t->job.mu_dt = (o.r - 0.5 * o.v * o.v) * dt;  // geomBrownian, DP/MonteCarloKernel.cu:104-107
@@ -833,6 +843,33 @@ int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint3
     cudaFree(d_out);
     if (e != cudaSuccess)
         return fail_cuda(ctx, e, "debug_normals");
+    return MCB200_OK;
+}
+
+int mcb200_debug_math64(mcb200_ctx *ctx, int fn, uint64_t n, const double *in_host, double *out_host)
+{
+    if (!ctx || !in_host || !out_host || n == 0 || fn < 0 || fn > 4)
+        return MCB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    double *d_in = nullptr, *d_out = nullptr;
+    MCB_CUDA(ctx, cudaMalloc(&d_in, n * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_out, 2 * n * sizeof(double));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_in, in_host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = debug_math64(fn, n, d_in, d_out, ctx->stream);
+    if (e == cudaSuccess) {
+        ctx->launches++;
+        e = cudaMemcpyAsync(out_host, d_out, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess)
+        return fail_cuda(ctx, e, "debug_math64");
     return MCB200_OK;
 }
 

@@ -85,13 +85,15 @@ struct Basket {
     using Table = BasketTable<Real, N, kFull>;
     static_assert(sizeof(Table) <= kBasketTableBytes, "basket table exceeds its constant buffer");
     static constexpr int kUnitPaths = 1;
+    static constexpr int kUnroll = 1;
     static constexpr int kMinBlocks = basket_min_blocks(N, (int)sizeof(Real));
     static constexpr int kNpb = NormalsPerBlock<Real>::value;
     struct Params {
         PhiloxKeys keys;
     };
-    static __device__ __forceinline__ float grow(float x) { return mufu_ex2(x); }
-    static __device__ __forceinline__ double grow(double x) { return exp(x); }
+    using Shared = typename SharedFor<Real>::type;
+    static __device__ __forceinline__ float grow(float x, const NoShared &) { return mufu_ex2(x); }
+    static __device__ __forceinline__ double grow(double x, const SharedTables64 &sh) { return exp_tab(x, sh.t); }
     static constexpr int kBlocks = (N + kNpb - 1) / kNpb;
     static constexpr int kFactorBase = 0;
     static constexpr int kABase = Table::kFactor * (int)sizeof(Real);
@@ -116,12 +118,13 @@ struct Basket {
     }
     // draw block JB: one Philox block -> kNpb normals -> kNpb columns
     template <int JB>
-    static __device__ __forceinline__ void draw_block(const Params &P, unsigned long long path, Real (&x)[N])
+    static __device__ __forceinline__ void draw_block(const Params &P, unsigned long long path, Real (&x)[N],
+                                                      const Shared &sh)
     {
         uint32_t w[4];
         philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)JB, kTagBasket, P.keys, w);
         Real z[kNpb];
-        normals_from_words(w, z);
+        normals_from_words(w, z, sh);
         column_if<JB * kNpb + 0>(x, z[0]);
         column_if<JB * kNpb + 1>(x, z[1]);
         if constexpr (kNpb == 4) {
@@ -131,9 +134,9 @@ struct Basket {
     }
     template <int... kJB>
     static __device__ __forceinline__ void sweep(const Params &P, unsigned long long path, Real (&x)[N],
-                                                 std::integer_sequence<int, kJB...>)
+                                                 const Shared &sh, std::integer_sequence<int, kJB...>)
     {
-        (draw_block<kJB>(P, path, x), ...);
+        (draw_block<kJB>(P, path, x, sh), ...);
     }
     template <int... kI>
     static __device__ __forceinline__ void init(Real (&x)[N], std::integer_sequence<int, kI...>)
@@ -141,18 +144,20 @@ struct Basket {
         ((x[kI] = table_entry<Real, kABase + kI * (int)sizeof(Real)>()), ...);
     }
     template <int... kI>
-    static __device__ __forceinline__ Real payoff(const Real (&x)[N], std::integer_sequence<int, kI...>)
+    static __device__ __forceinline__ Real payoff(const Real (&x)[N], const Shared &sh,
+                                                  std::integer_sequence<int, kI...>)
     {
         Real sum = -table_entry<Real, kKBase>();
-        ((sum = fma(table_entry<Real, kMBase + kI * (int)sizeof(Real)>(), grow(x[kI]), sum)), ...);
-        return fmax(sum, (Real)0);
+        ((sum = fma(table_entry<Real, kMBase + kI * (int)sizeof(Real)>(), grow(x[kI], sh), sum)), ...);
+        return positive_part(sum);
     }
-    static __device__ __forceinline__ void eval(const Params &P, unsigned long long path, Real (&v)[1])
+    static __device__ __forceinline__ void eval(const Params &P, unsigned long long path, Real (&v)[1],
+                                                const Shared &sh)
     {
         Real x[N];
         init(x, std::make_integer_sequence<int, N>{});
-        sweep(P, path, x, std::make_integer_sequence<int, kBlocks>{});
-        v[0] = payoff(x, std::make_integer_sequence<int, N>{});
+        sweep(P, path, x, sh, std::make_integer_sequence<int, kBlocks>{});
+        v[0] = payoff(x, sh, std::make_integer_sequence<int, N>{});
     }
 };
 

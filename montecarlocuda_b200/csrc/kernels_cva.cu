@@ -46,10 +46,20 @@ __device__ __forceinline__ Real hastings_tail(Real d, Real pdf)
     return pdf * (k * poly);
 }
 
+// max(a, -700) for a <= 0 without touching the fp64 pipe: negative doubles order like their high
+// words taken as unsigned integers, so one integer min on the high word does it (-inf included).
+__device__ __forceinline__ double floor_at_minus_700(double a)
+{
+    const unsigned hi = min((unsigned)__double2hiint(a), 0xC085E000u);  // high word of -700.0
+    return __hiloint2double((int)hi, hi == 0xC085E000u ? 0 : __double2loint(a));
+}
+__device__ __forceinline__ float floor_at_minus_700(float a) { return a; }  // MUFU.EX2(-inf) = 0
+
 template <typename RealT>
 struct Cva {
     using Real = RealT;
     static constexpr int kUnitPaths = 1;
+    static constexpr int kUnroll = 1;
     static constexpr int kMinBlocks = 3;
     static constexpr int kNpb = NormalsPerBlock<Real>::value;
     struct Params {
@@ -57,14 +67,17 @@ struct Cva {
         Real y0, mu_dt, sig_dt, k;
         int n_dates;  // kept dates
     };
+    using Shared = typename SharedFor<Real>::type;
     static __device__ __forceinline__ void step(const Params &P, const CvaDate<Real> &D, Real z, Real &y,
-                                                Real &cva)
+                                                Real &cva, const Shared &sh)
     {
         y = fma(P.sig_dt, z, y + P.mu_dt);
-        const Real s = P.k * exp_real(y);
+        const Real s = P.k * exp_real(y, sh);
         const Real d1 = fma(y, D.inv, D.c1);
         const Real d2 = d1 - D.sig;
-        const Real pdf1 = (Real)0.39894228040143267793994605993438 * exp_real((Real)-0.5 * d1 * d1);
+        // -d1^2/2 can be -1e14 (a date a few ulps before maturity) or -inf (exact grid, tau = 0):
+        // floor it where e^x is already 0 for every purpose, so the table-driven exp stays in range
+        const Real pdf1 = (Real)0.39894228040143267793994605993438 * exp_real(floor_at_minus_700((Real)-0.5 * d1 * d1), sh);
         const Real pdf2 = pdf1 * s * D.rkd;
         const Real t1 = hastings_tail(d1, pdf1);
         const Real t2 = hastings_tail(d2, pdf2);
@@ -73,7 +86,8 @@ struct Cva {
         const Real ee = s * n1 - D.kd * n2;
         cva = fma(D.w, ee, cva);
     }
-    static __device__ __forceinline__ void eval(const Params &P, unsigned long long path, Real (&v)[1])
+    static __device__ __forceinline__ void eval(const Params &P, unsigned long long path, Real (&v)[1],
+                                                const Shared &sh)
     {
         const CvaDate<Real> *dates = reinterpret_cast<const CvaDate<Real> *>(c_cva_table);
         Real y = P.y0, cva = 0;
@@ -82,12 +96,12 @@ struct Cva {
             uint32_t w[4];
             philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)jb, kTagCva, P.keys, w);
             Real z[kNpb];
-            normals_from_words(w, z);
+            normals_from_words(w, z, sh);
 #pragma unroll
             for (int q = 0; q < kNpb; q++) {
                 const int j = jb * kNpb + q;
                 if (j < P.n_dates)
-                    step(P, dates[j], z[q], y, cva);
+                    step(P, dates[j], z[q], y, cva, sh);
             }
         }
         v[0] = cva;

@@ -24,12 +24,15 @@ template <typename Real, int kPerBlock>
 __global__ void debug_normals_kernel(unsigned long long n, const uint32_t *__restrict__ ctr,
                                      const __grid_constant__ PhiloxKeys keys, Real *__restrict__ out)
 {
+    __shared__ typename SharedFor<Real>::type sh;
+    sh.load();
+    __syncthreads();
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t w[4];
         philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], keys, w);
         Real z[kPerBlock];
-        normals_from_words(w, z);
+        normals_from_words(w, z, sh);
 #pragma unroll
         for (int q = 0; q < kPerBlock; q++)
             out[kPerBlock * i + q] = z[q];
@@ -72,6 +75,30 @@ debug_reduce_kernel(const double *__restrict__ values, unsigned long long n_vali
     scratch_flush(sc, acc);
 }
 
+// The fp64 special functions on their own: fn 0 = -2 ln(u), 1 = sqrt, 2 = 1/x, 3 = e^x,
+// 4 = cos/sin of 2 pi k / 2^52 (input reinterpreted as the 52-bit integer k; two outputs).
+__global__ void debug_math64_kernel(int fn, unsigned long long n, const double *__restrict__ in,
+                                    double *__restrict__ out)
+{
+    __shared__ SharedTables64 sh;
+    sh.load();
+    __syncthreads();
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const double x = in[i];
+        double a = 0, b = 0;
+        switch (fn) {
+            case 0: a = neg2log_unit(x, sh.t); break;
+            case 1: a = sqrt_pos(x); break;
+            case 2: a = rcp_newton(x); break;
+            case 3: a = exp_tab(x, sh.t); break;
+            default: sincos_turn((uint32_t)__double2hiint(x), (uint32_t)__double2loint(x), a, b); break;
+        }
+        out[2 * i] = a;
+        out[2 * i + 1] = b;
+    }
+}
+
 static int grid_for(unsigned long long n)
 {
     const unsigned long long blocks = (n + kThreads - 1) / kThreads;
@@ -92,6 +119,12 @@ cudaError_t debug_normals(int precision, unsigned long long n, const uint32_t *d
         debug_normals_kernel<double, 2><<<grid_for(n), kThreads, 0, stream>>>(n, d_ctr, keys, (double *)d_out);
     else
         debug_normals_kernel<float, 4><<<grid_for(n), kThreads, 0, stream>>>(n, d_ctr, keys, (float *)d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t debug_math64(int fn, unsigned long long n, const double *d_in, double *d_out, cudaStream_t stream)
+{
+    debug_math64_kernel<<<grid_for(n), kThreads, 0, stream>>>(fn, n, d_in, d_out);
     return cudaGetLastError();
 }
 

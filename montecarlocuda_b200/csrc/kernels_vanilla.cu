@@ -6,40 +6,10 @@
 //   fp32: payoff = max(2^(a + b z) - K, 0),  a = log2(S0) + (r - v^2/2) T log2(e),  b = v sqrt(T) log2(e)
 //   fp64: payoff = max(e^(a + b z) - K, 0),  a = ln(S0) + (r - v^2/2) T,            b = v sqrt(T)
 // so a path costs one FMA and one exponential after its normal.
-#include "device_math.cuh"
 #include "launch.h"
+#include "workload_vanilla.cuh"
 
 namespace mcb {
-
-template <typename Real> struct NormalsPerBlock;
-template <> struct NormalsPerBlock<float> { static constexpr int value = 4; };
-template <> struct NormalsPerBlock<double> { static constexpr int value = 2; };
-
-template <typename RealT>
-struct Vanilla {
-    using Real = RealT;
-    static constexpr int kUnitPaths = NormalsPerBlock<Real>::value;
-    static constexpr int kMinBlocks = 4;
-    struct Params {
-        PhiloxKeys keys;
-        Real a, b, k;
-    };
-    static __device__ __forceinline__ float grow(float x) { return mufu_ex2(x); }
-    static __device__ __forceinline__ double grow(double x) { return exp(x); }
-    static __device__ __forceinline__ void eval(const Params &P, unsigned long long unit,
-                                                Real (&v)[kUnitPaths])
-    {
-        uint32_t w[4];
-        philox4x32_10((uint32_t)unit, (uint32_t)(unit >> 32), 0u, kTagVanilla, P.keys, w);
-        Real z[kUnitPaths];
-        normals_from_words(w, z);
-#pragma unroll
-        for (int q = 0; q < kUnitPaths; q++) {
-            const Real st = grow(fma(P.b, z[q], P.a));
-            v[q] = fmax(st - P.k, (Real)0);
-        }
-    }
-};
 
 template <typename Real>
 static typename Vanilla<Real>::Params narrow(const VanillaJob &job)

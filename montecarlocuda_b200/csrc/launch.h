@@ -59,6 +59,7 @@ cudaError_t debug_philox(unsigned long long n, const uint32_t *d_ctr, PhiloxKeys
                          cudaStream_t stream);
 cudaError_t debug_normals(int precision, unsigned long long n, const uint32_t *d_ctr, PhiloxKeys keys,
                           void *d_out, cudaStream_t stream);
+cudaError_t debug_math64(int fn, unsigned long long n, const double *d_in, double *d_out, cudaStream_t stream);
 cudaError_t debug_reduce(const double *d_values, unsigned long long n_valid, int unit_paths, int rounds,
                          bool accumulate_in_float, int scale_exp_sum, int scale_exp_sumsq,
                          unsigned long long *d_acc, cudaStream_t stream);

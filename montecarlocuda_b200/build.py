@@ -103,7 +103,7 @@ def build_oracle(verbose: bool = False) -> None:
     the unmodified reference into oracle/_ref/.  Building the checker is not using it."""
     _run(["make", "-C", ROOT / "oracle", "oracle"], verbose)
     if Path("/root/reference/double_precision/MonteCarloHost.c").exists():
-        _run(["make", "-C", ROOT / "oracle", "ref"], verbose)
+        _run(["make", "-C", ROOT / "oracle", "ref", "drivers"], verbose)
 
 
 if __name__ == "__main__":

@@ -54,21 +54,54 @@ template <typename Real, int kByteOffset> __device__ __forceinline__ Real table_
         return table_entry_f64<kByteOffset>();
 }
 
+// x2 = {lo, hi} += table pair at kByteOffset * {z, z}: one FFMA2 (fma.rn.f32x2, new in sm_100).
+// The packed FMA keeps the FP32 pipe at 128 FMA/clk/SM with HALF the issue slots, and the freed
+// slots are where the Philox LOP3s, the uniform loads and the MUFU ops of the next normals issue
+// (profiles/r01_pipe_ffma2.txt: FFMA2 x8 + LOP3 x4 costs the same 16.2 cycles as FFMA2 x8 alone).
+template <int kByteOffset>
+__device__ __forceinline__ void packed_fma_entry(unsigned long long &x2, unsigned long long zz)
+{
+    asm volatile("{\n\t.reg .b64 f;\n\tld.const.b64 f, [mcb_basket_table+%2];\n\tfma.rn.f32x2 %0, f, %1, %0;\n\t}"
+                 : "+l"(x2)
+                 : "l"(zz), "n"(kByteOffset));
+}
+template <int kByteOffset>
+__device__ __forceinline__ unsigned long long table_pair()
+{
+    unsigned long long t;
+    asm volatile("ld.const.b64 %0, [mcb_basket_table+%1];" : "=l"(t) : "n"(kByteOffset));
+    return t;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
 template <typename Real> struct NormalsPerBlock;
 template <> struct NormalsPerBlock<float> { static constexpr int value = 4; };
 template <> struct NormalsPerBlock<double> { static constexpr int value = 2; };
 
+// Table layout.  Column-major; column `col` holds rows first_row(col) .. N-1.  fp32 with an even
+// width runs on packed FMAs (FFMA2, two rows per instruction), so its columns start on an even row
+// (the extra entry above the diagonal of an odd column is an exact 0) and every pair is 8-byte
+// aligned; fp64 and odd widths keep the plain packed triangle.
 template <typename Real, int N, bool kFull>
 struct BasketTable {
-    static constexpr int kFactor = kFull ? N * N : N * (N + 1) / 2;
-    Real factor[kFactor];  // column-major; packed lower triangle unless kFull
+    static constexpr bool kPaired = sizeof(Real) == 4 && N % 2 == 0;
+    static __host__ __device__ constexpr int first_row(int col) { return kFull ? 0 : (kPaired ? (col & ~1) : col); }
+    static __host__ __device__ constexpr int column_start(int col)
+    {
+        int off = 0;
+        for (int c = 0; c < col; c++)
+            off += N - first_row(c);
+        return off;
+    }
+    static constexpr int kFactor = column_start(N);
+    Real factor[kFactor];
     Real a[N];
     Real m[N];
     Real k;
-    static __host__ __device__ constexpr int index(int col, int row)
-    {
-        return kFull ? col * N + row : col * N - col * (col - 1) / 2 + (row - col);
-    }
+    static __host__ __device__ constexpr int index(int col, int row) { return column_start(col) + (row - first_row(col)); }
 };
 
 constexpr int basket_min_blocks(int n, int real_bytes)
@@ -100,64 +133,90 @@ struct Basket {
     static constexpr int kMBase = kABase + N * (int)sizeof(Real);
     static constexpr int kKBase = kMBase + N * (int)sizeof(Real);
 
-    // column J of the sweep: x[row] += F[row][J] * z for row = first .. N-1
+    static constexpr bool kPaired = Table::kPaired;
+    // accumulators: N scalars, or N/2 packed pairs for the FFMA2 path
+    struct State {
+        Real x[kPaired ? 1 : N];
+        unsigned long long x2[kPaired ? N / 2 : 1];
+    };
+
+    // column J of the sweep: x[row] += F[row][J] * z for row = first_row(J) .. N-1
     template <int J, int... kRow>
-    static __device__ __forceinline__ void column(Real (&x)[N], Real z, std::integer_sequence<int, kRow...>)
+    static __device__ __forceinline__ void column(State &st, Real z, std::integer_sequence<int, kRow...>)
     {
-        constexpr int first = kFull ? 0 : J;
-        ((x[first + kRow] =
-              fma(table_entry<Real, kFactorBase + Table::index(J, first + kRow) * (int)sizeof(Real)>(), z,
-                  x[first + kRow])),
-         ...);
+        constexpr int first = Table::first_row(J);
+        if constexpr (kPaired) {
+            // (a deeper software pipeline of the table loads was tried: ptxas re-sinks every LDCU.128
+            // next to its two FFMA2s whatever the source order, it keeps two uniform quads in flight)
+            const unsigned long long zz = pack2(z, z);
+            (packed_fma_entry<kFactorBase + Table::index(J, first + 2 * kRow) * 4>(st.x2[first / 2 + kRow], zz), ...);
+        } else {
+            ((st.x[first + kRow] =
+                  fma(table_entry<Real, kFactorBase + Table::index(J, first + kRow) * (int)sizeof(Real)>(), z,
+                      st.x[first + kRow])),
+             ...);
+        }
     }
     template <int J>
-    static __device__ __forceinline__ void column_if(Real (&x)[N], Real z)
+    static __device__ __forceinline__ void column_if(State &st, Real z)
     {
-        if constexpr (J < N)
-            column<J>(x, z, std::make_integer_sequence<int, (kFull ? N : N - J)>{});
+        if constexpr (J < N) {
+            constexpr int rows = N - Table::first_row(J);
+            column<J>(st, z, std::make_integer_sequence<int, (kPaired ? rows / 2 : rows)>{});
+        }
     }
     // draw block JB: one Philox block -> kNpb normals -> kNpb columns
     template <int JB>
-    static __device__ __forceinline__ void draw_block(const Params &P, unsigned long long path, Real (&x)[N],
+    static __device__ __forceinline__ void draw_block(const Params &P, unsigned long long path, State &st,
                                                       const Shared &sh)
     {
         uint32_t w[4];
         philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)JB, kTagBasket, P.keys, w);
         Real z[kNpb];
         normals_from_words(w, z, sh);
-        column_if<JB * kNpb + 0>(x, z[0]);
-        column_if<JB * kNpb + 1>(x, z[1]);
+        column_if<JB * kNpb + 0>(st, z[0]);
+        column_if<JB * kNpb + 1>(st, z[1]);
         if constexpr (kNpb == 4) {
-            column_if<JB * kNpb + 2>(x, z[2]);
-            column_if<JB * kNpb + 3>(x, z[3]);
+            column_if<JB * kNpb + 2>(st, z[2]);
+            column_if<JB * kNpb + 3>(st, z[3]);
         }
     }
     template <int... kJB>
-    static __device__ __forceinline__ void sweep(const Params &P, unsigned long long path, Real (&x)[N],
+    static __device__ __forceinline__ void sweep(const Params &P, unsigned long long path, State &st,
                                                  const Shared &sh, std::integer_sequence<int, kJB...>)
     {
-        (draw_block<kJB>(P, path, x, sh), ...);
+        (draw_block<kJB>(P, path, st, sh), ...);
     }
     template <int... kI>
-    static __device__ __forceinline__ void init(Real (&x)[N], std::integer_sequence<int, kI...>)
+    static __device__ __forceinline__ void init(State &st, std::integer_sequence<int, kI...>)
     {
-        ((x[kI] = table_entry<Real, kABase + kI * (int)sizeof(Real)>()), ...);
+        if constexpr (kPaired)
+            ((st.x2[kI] = table_pair<kABase + kI * 8>()), ...);
+        else
+            ((st.x[kI] = table_entry<Real, kABase + kI * (int)sizeof(Real)>()), ...);
+    }
+    template <int I>
+    static __device__ __forceinline__ Real exponent(const State &st)
+    {
+        if constexpr (kPaired)
+            return __uint_as_float((uint32_t)(st.x2[I / 2] >> (32 * (I % 2))));
+        else
+            return st.x[I];
     }
     template <int... kI>
-    static __device__ __forceinline__ Real payoff(const Real (&x)[N], const Shared &sh,
-                                                  std::integer_sequence<int, kI...>)
+    static __device__ __forceinline__ Real payoff(const State &st, const Shared &sh, std::integer_sequence<int, kI...>)
     {
         Real sum = -table_entry<Real, kKBase>();
-        ((sum = fma(table_entry<Real, kMBase + kI * (int)sizeof(Real)>(), grow(x[kI], sh), sum)), ...);
+        ((sum = fma(table_entry<Real, kMBase + kI * (int)sizeof(Real)>(), grow(exponent<kI>(st), sh), sum)), ...);
         return positive_part(sum);
     }
     static __device__ __forceinline__ void eval(const Params &P, unsigned long long path, Real (&v)[1],
                                                 const Shared &sh)
     {
-        Real x[N];
-        init(x, std::make_integer_sequence<int, N>{});
-        sweep(P, path, x, sh, std::make_integer_sequence<int, kBlocks>{});
-        v[0] = payoff(x, sh, std::make_integer_sequence<int, N>{});
+        State st;
+        init(st, std::make_integer_sequence<int, (kPaired ? N / 2 : N)>{});
+        sweep(P, path, st, sh, std::make_integer_sequence<int, kBlocks>{});
+        v[0] = payoff(st, sh, std::make_integer_sequence<int, N>{});
     }
 };
 
@@ -171,7 +230,7 @@ static void fill_table(const BasketJob &job, BasketTable<Real, N, kFull> &T)
     for (int i = 0; i < Table::kFactor; i++)
         T.factor[i] = 0;
     for (int col = 0; col < N; col++)
-        for (int row = (kFull ? 0 : col); row < N; row++) {
+        for (int row = Table::first_row(col); row < N; row++) {
             const double f = (row < job.n && col < job.n) ? job.factor[row * job.n + col] : 0.0;
             T.factor[Table::index(col, row)] = (Real)(f * unit);
         }

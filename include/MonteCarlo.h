@@ -100,6 +100,24 @@ OptionValue dev_vanillaOpt(OptionData *opt, int numBlocks, int numThreads, int s
 OptionValue dev_basketOpt(MultiOptionData *option, int numBlocks, int numThreads, int sims);
 OptionValue dev_cvaEquityOption(CVA *cva, int numBlocks, int numThreads, int sims);
 
+/* ---- host helpers (reference MonteCarloHost.c:20-143, 282-311), libmcb200_hostapi_{dp,sp}[_nN].so ----
+ * CPU-side companions the reference drivers import next to the GPU entry points.  They are NOT on the
+ * GPU pricing path and the dev_* functions never fall back to them (see csrc/hostapi.c). */
+void printVect(mc_real *mat, int c);
+void printMat(mc_real *mat, int r, int c);
+void printOption(OptionData o);
+void printMultiOpt(MultiOptionData *o);
+void prodMat(mc_real *first, mc_real *second, mc_real *result, int f_rows, int f_cols, int s_cols);
+void Chol(mc_real c[N][N], mc_real a[N][N]);
+mc_real randMinMax(mc_real min, mc_real max);
+mc_real host_bsCall(OptionData option);
+OptionValue host_vanillaOpt(OptionData option, int path);
+OptionValue host_basketOpt(MultiOptionData *option, int path);
+OptionValue host_cvaEquityOption(CVA *cva, int path);
+/* runtime-width Cholesky that REPORTS a non-positive pivot (returns its 1-based index, 0 = success)
+ * instead of silently zeroing the column as Chol does (MonteCarloHost.c:100-101) */
+int mcb200_chol(int n, const double *c, double *a);
+
 #ifdef __cplusplus
 }
 #endif

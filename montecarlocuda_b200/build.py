@@ -90,6 +90,27 @@ def build(verbose: bool = False, force: bool = False) -> Path:
                 _run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", f"-DN={n}"] + define +
                      ["-I", INCLUDE, shim_src, "-o", out, f"-L{LIB}", "-lmcb200", "-Wl,-rpath,$ORIGIN"], verbose)
 
+    # the reference's CPU helper API (pure C, no CUDA) and the non-interactive CLI drivers
+    host_src = CSRC / "hostapi.c"
+    cc = shutil.which("gcc") or "gcc"
+    for prec, define in (("dp", []), ("sp", ["-DMCB200_SINGLE"])):
+        for n in DROPIN_WIDTHS:
+            suffix = f"{prec}" if n == 3 else f"{prec}_n{n}"
+            out = LIB / f"libmcb200_hostapi_{suffix}.so"
+            if force or _newer(out, [host_src, INCLUDE / "MonteCarlo.h", Path(__file__)]):
+                _run([cc, "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-ffp-contract=off", f"-DN={n}"] + define +
+                     ["-I", INCLUDE, host_src, "-o", out, "-lm"], verbose)
+            for app in ("vanillaOpt", "basketOpt", "cvaOpt"):
+                src = CSRC / "apps" / f"{app}.c"
+                if not src.exists() or (app != "basketOpt" and n != 3):
+                    continue
+                exe = LIB / f"mcb200_{app}_{suffix}"
+                deps = [src, CSRC / "apps" / "cli_common.h", INCLUDE / "MonteCarlo.h", INCLUDE / "mcb200.h", out, Path(__file__)]
+                if force or _newer(exe, deps):
+                    dropin = "mcb200_" + suffix
+                    _run([cc, "-O2", "-std=gnu11", "-Wall", f"-DN={n}"] + define + ["-I", INCLUDE, src, "-o", exe, f"-L{LIB}",
+                         f"-l{dropin}", f"-lmcb200_hostapi_{suffix}", "-lmcb200", "-lm", "-Wl,-rpath,$ORIGIN"], verbose)
+
     peaks_src = CSRC / "pipe_peaks.cu"
     if peaks_src.exists():
         peaks = LIB / "pipe_peaks"

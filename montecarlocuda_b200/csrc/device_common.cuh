@@ -140,7 +140,9 @@ __device__ __forceinline__ void scratch_flush(const BlockScratch &sc, unsigned l
 //   W::kUnitPaths      paths served by one draw unit
 //   W::kMinBlocks      CTAs per SM the register budget is sized for; W::kUnroll  unroll of the unit loop
 //   W::Shared          per-CTA shared-memory state (the fp64 math tables; empty for fp32)
-//   W::eval(P, unit, v, sh) fills v[kUnitPaths] with the per-path values of draw unit `unit`
+//   W::eval(P, unit_lo, unit_hi, v, sh) fills v[kUnitPaths] with the per-path values of a draw unit;
+//                      inside a chunk unit_hi is the same for every thread (chunks are aligned), so the
+//                      part of the first two Philox rounds that depends only on it runs on the uniform datapath
 // A CTA walks chunks first_chunk + blockIdx.x, + gridDim.x, ...; thread t of a chunk owns units
 // base + k * 256 + t for k < rounds, in that order, and accumulates value and value^2 in W::Real
 // (short runs: at most rounds * kUnitPaths <= 256 terms) before the fp64 block reduction.
@@ -176,7 +178,7 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
                 if (W::kUnitPaths == 1 && !whole && unit >= G.total_paths)
                     break;
                 Real v[W::kUnitPaths];
-                W::eval(P, unit, v, sh);
+                W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + threadIdx.x, (uint32_t)(base >> 32), v, sh);
 #pragma unroll
                 for (int q = 0; q < W::kUnitPaths; q++) {
                     s += v[q];
@@ -191,7 +193,7 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
                 if (unit * (unsigned long long)W::kUnitPaths >= G.total_paths)
                     break;
                 Real v[W::kUnitPaths];
-                W::eval(P, unit, v, sh);
+                W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + threadIdx.x, (uint32_t)(base >> 32), v, sh);
 #pragma unroll
                 for (int q = 0; q < W::kUnitPaths; q++) {
                     if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths) {
@@ -218,7 +220,7 @@ mc_paths_kernel(const __grid_constant__ typename W::Params P, unsigned long long
     for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n_units;
          i += (unsigned long long)gridDim.x * kThreads) {
         typename W::Real v[W::kUnitPaths];
-        W::eval(P, first_unit + i, v, sh);
+        W::eval(P, (uint32_t)(first_unit + i), (uint32_t)((first_unit + i) >> 32), v, sh);
 #pragma unroll
         for (int q = 0; q < W::kUnitPaths; q++)
             out[i * W::kUnitPaths + q] = v[q];

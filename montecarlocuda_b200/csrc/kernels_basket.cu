@@ -167,11 +167,11 @@ struct Basket {
     }
     // draw block JB: one Philox block -> kNpb normals -> kNpb columns
     template <int JB>
-    static __device__ __forceinline__ void draw_block(const Params &P, unsigned long long path, State &st,
+    static __device__ __forceinline__ void draw_block(const Params &P, uint32_t path_lo, uint32_t path_hi, State &st,
                                                       const Shared &sh)
     {
         uint32_t w[4];
-        philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)JB, kTagBasket, P.keys, w);
+        philox4x32_10(path_lo, path_hi, (uint32_t)JB, kTagBasket, P.keys, w);
         Real z[kNpb];
         normals_from_words(w, z, sh);
         column_if<JB * kNpb + 0>(st, z[0]);
@@ -182,10 +182,10 @@ struct Basket {
         }
     }
     template <int... kJB>
-    static __device__ __forceinline__ void sweep(const Params &P, unsigned long long path, State &st,
+    static __device__ __forceinline__ void sweep(const Params &P, uint32_t path_lo, uint32_t path_hi, State &st,
                                                  const Shared &sh, std::integer_sequence<int, kJB...>)
     {
-        (draw_block<kJB>(P, path, st, sh), ...);
+        (draw_block<kJB>(P, path_lo, path_hi, st, sh), ...);
     }
     template <int... kI>
     static __device__ __forceinline__ void init(State &st, std::integer_sequence<int, kI...>)
@@ -210,12 +210,12 @@ struct Basket {
         ((sum = fma(table_entry<Real, kMBase + kI * (int)sizeof(Real)>(), grow(exponent<kI>(st), sh), sum)), ...);
         return positive_part(sum);
     }
-    static __device__ __forceinline__ void eval(const Params &P, unsigned long long path, Real (&v)[1],
+    static __device__ __forceinline__ void eval(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
                                                 const Shared &sh)
     {
         State st;
         init(st, std::make_integer_sequence<int, (kPaired ? N / 2 : N)>{});
-        sweep(P, path, st, sh, std::make_integer_sequence<int, kBlocks>{});
+        sweep(P, path_lo, path_hi, st, sh, std::make_integer_sequence<int, kBlocks>{});
         v[0] = payoff(st, sh, std::make_integer_sequence<int, N>{});
     }
 };

@@ -86,7 +86,7 @@ struct Cva {
         const Real ee = s * n1 - D.kd * n2;
         cva = fma(D.w, ee, cva);
     }
-    static __device__ __forceinline__ void eval(const Params &P, unsigned long long path, Real (&v)[1],
+    static __device__ __forceinline__ void eval(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
                                                 const Shared &sh)
     {
         const CvaDate<Real> *dates = reinterpret_cast<const CvaDate<Real> *>(c_cva_table);
@@ -94,7 +94,7 @@ struct Cva {
 #pragma unroll 1
         for (int jb = 0; jb * kNpb < P.n_dates; jb++) {
             uint32_t w[4];
-            philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)jb, kTagCva, P.keys, w);
+            philox4x32_10(path_lo, path_hi, (uint32_t)jb, kTagCva, P.keys, w);
             Real z[kNpb];
             normals_from_words(w, z, sh);
 #pragma unroll

@@ -30,11 +30,11 @@ struct Vanilla {
     using Shared = typename SharedFor<Real>::type;
     static __device__ __forceinline__ float grow(float x, const NoShared &) { return mufu_ex2(x); }
     static __device__ __forceinline__ double grow(double x, const SharedTables64 &sh) { return exp_tab(x, sh.t); }
-    static __device__ __forceinline__ void eval(const Params &P, unsigned long long unit,
+    static __device__ __forceinline__ void eval(const Params &P, uint32_t unit_lo, uint32_t unit_hi,
                                                 Real (&v)[kUnitPaths], const Shared &sh)
     {
         uint32_t w[4];
-        philox4x32_10((uint32_t)unit, (uint32_t)(unit >> 32), 0u, kVanillaTag, P.keys, w);
+        philox4x32_10(unit_lo, unit_hi, 0u, kVanillaTag, P.keys, w);
         Real z[kUnitPaths];
         normals_from_words(w, z, sh);
 #pragma unroll

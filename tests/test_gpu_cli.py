@@ -29,7 +29,7 @@ def test_vanilla_cli(engine, precision):
     f, out = run(f"mcb200_vanillaOpt_{precision}", "--sims", 1 << 22, "--cpu-sims", 1 << 18)
     assert "Underlying asset price" in out                           # printOption, as the reference driver
     bs, gpu, conf = f["black_scholes_price"][0], f["gpu_price"][0], f["gpu_confidence"][0]
-    assert bs == pytest.approx(10.386271, abs=2e-6)
+    assert bs == pytest.approx(10.386271, abs=1.5e-5)    # Hastings cnd: 10.386262 vs exact 10.386271 (Q11)
     assert abs(gpu - bs) < 4 * conf / 1.96 and f["gpu_difference_from_bs"][0] == pytest.approx(abs(gpu - bs), abs=2e-6)
     assert abs(f["cpu_price"][0] - bs) < 4 * f["cpu_confidence"][0] / 1.96
     assert f["gpu_sims"][0] == 1 << 22 and f["speedup_per_path"][0] > 10

@@ -82,7 +82,7 @@ def test_reference_drivers_with_no_reference_object(engine, oracle):
     bs = floats_after(out, "Prezzo Black & Scholes:", 1)[0]
     cpu = floats_after(out, "Expected price, I.C., time", 2)
     gpu = re.search(r"Simulated price for the option with GPU:.*?\n128 \n([-\d.]+) \n([-\d.]+) \n", out, re.S)
-    assert bs == pytest.approx(10.386271, abs=2e-6)                   # driver's r = 0.048790
+    assert bs == pytest.approx(10.386271, abs=1.5e-5)                  # driver's r = 0.048790
     assert abs(cpu[0] - bs) < 4 * cpu[1] / 1.96 and abs(float(gpu.group(1)) - bs) < 4 * float(gpu.group(2)) / 1.96
     # same Philox stream on both sides of the driver: CPU and GPU estimates agree far inside Monte Carlo error
     assert abs(cpu[0] - float(gpu.group(1))) < 2e-6

@@ -251,13 +251,17 @@ static cudaError_t launch_t(const BasketJob &job, const Geometry *geom, int grid
     fill_table(job, *reinterpret_cast<typename W::Table *>(staging.data()));
     typename W::Params p;
     p.keys = job.keys;
-    TableUse use(g_basket_lock, stream);
+    TableUse use(g_basket_lock, stream, staging.data(), staging.size());
     if (use.status() != cudaSuccess)
         return use.status();
-    cudaError_t e = cudaMemcpyToSymbolAsync(mcb_basket_table, staging.data(), staging.size(), 0,
-                                            cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess)
-        return e;
+    if (use.needs_upload()) {
+        cudaError_t e = cudaMemcpyToSymbolAsync(mcb_basket_table, staging.data(), staging.size(), 0,
+                                                cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) {
+            use.invalidate();
+            return e;
+        }
+    }
     if (geom) {
         mc_accumulate_kernel<W><<<grid, kThreads, 0, stream>>>(p, *geom, d_acc);
     } else {

@@ -133,13 +133,17 @@ static cudaError_t launch_t(const CvaJob &job, const Geometry *geom, int grid, u
         const CvaDateHost &h = job.dates[j];
         staging[j] = CvaDate<Real>{(Real)h.w, (Real)h.inv, (Real)h.c1, (Real)h.sig, (Real)h.kd, (Real)h.rkd};
     }
-    TableUse use(g_cva_lock, stream);
+    TableUse use(g_cva_lock, stream, staging.data(), staging.size() * sizeof(CvaDate<Real>));
     if (use.status() != cudaSuccess)
         return use.status();
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_cva_table, staging.data(), staging.size() * sizeof(CvaDate<Real>), 0,
-                                            cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess)
-        return e;
+    if (use.needs_upload()) {
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_cva_table, staging.data(), staging.size() * sizeof(CvaDate<Real>), 0,
+                                                cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) {
+            use.invalidate();
+            return e;
+        }
+    }
     if (geom) {
         mc_accumulate_kernel<Cva<Real>><<<grid, kThreads, 0, stream>>>(narrow<Real>(job), *geom, d_acc);
     } else {

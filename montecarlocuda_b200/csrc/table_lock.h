@@ -6,7 +6,9 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace mcb {
 
@@ -15,19 +17,35 @@ struct TableLock {
     std::mutex mu;
     cudaEvent_t last_use[kMaxDevices] = {};
     bool used[kMaxDevices] = {};
+    // what the device's table holds once everything enqueued so far has run: a job repeated with the
+    // same parameters skips the upload
+    std::vector<unsigned char> resident[kMaxDevices];
 };
 
 class TableUse {
 public:
-    TableUse(TableLock &lock, cudaStream_t stream) : lock_(lock), stream_(stream)
+    // `bytes`/`size`: the table image this job needs.  needs_upload() tells the caller whether the
+    // device copy differs.
+    TableUse(TableLock &lock, cudaStream_t stream, const void *bytes, size_t size) : lock_(lock), stream_(stream)
     {
         lock_.mu.lock();
         status_ = cudaGetDevice(&device_);
         if (status_ == cudaSuccess && (device_ < 0 || device_ >= TableLock::kMaxDevices))
             status_ = cudaErrorInvalidDevice;
-        if (status_ == cudaSuccess && lock_.used[device_])
+        if (status_ != cudaSuccess)
+            return;
+        std::vector<unsigned char> &res = lock_.resident[device_];
+        upload_ = res.size() != size || std::memcmp(res.data(), bytes, size) != 0;
+        if (upload_)
+            res.assign((const unsigned char *)bytes, (const unsigned char *)bytes + size);
+        // always ordered after the table's previous user: its upload may still be in flight on
+        // another stream (free when it is the same stream)
+        if (lock_.used[device_])
             status_ = cudaStreamWaitEvent(stream_, lock_.last_use[device_], 0);
     }
+    bool needs_upload() const { return upload_; }
+    // the upload or launch failed: the device copy is unknown
+    void invalidate() { if (device_ >= 0 && device_ < TableLock::kMaxDevices) lock_.resident[device_].clear(); }
     ~TableUse()
     {
         if (status_ == cudaSuccess) {
@@ -47,6 +65,7 @@ private:
     cudaStream_t stream_;
     int device_ = -1;
     cudaError_t status_ = cudaSuccess;
+    bool upload_ = true;
 };
 
 }  // namespace mcb

@@ -41,6 +41,8 @@ def _launch(engine: Engine, workload: str, p: _lib.PlanT, params, seed: int, fir
 class ShardedPricer:
     """One rank's view of a sharded pricing job: persistent engine + device accumulator."""
 
+    RING = 32
+
     def __init__(self, engine: Engine | None = None, device: int | None = None, group=None):
         import torch
 
@@ -50,8 +52,13 @@ class ShardedPricer:
         self.device = torch.device("cuda", device)
         self.engine = engine or Engine(device)
         self.group = group
-        self.acc = torch.zeros(_lib.ACC_WORDS, dtype=torch.int64, device=self.device)
+        # a ring of accumulator blocks zeroed in one memset every RING steps (no memset kernel per step)
+        self.ring = torch.zeros((self.RING, _lib.ACC_WORDS), dtype=torch.int64, device=self.device)
+        self.slot = 0
+        self.acc = self.ring[0]
         self.host = torch.zeros(_lib.ACC_WORDS, dtype=torch.int64).pin_memory()
+        self._job_key = None
+        self._job = None
 
     def _world(self):
         import torch.distributed as dist
@@ -63,13 +70,23 @@ class ShardedPricer:
     def enqueue(self, workload: str, params, n_paths: int, precision=_lib.F64, seed: int = DEFAULT_SEED):
         """Asynchronously: zero the accumulator, run this rank's shard, all-reduce.  Returns the plan."""
         torch = self.torch
-        rank, world = self._world()
-        p = plan(workload, params, n_paths, precision)
-        first, count = shard_range(p, rank, world)
+        key = (workload, id(params), n_paths, precision, seed)
+        if key != self._job_key:        # plan, shard range and C structs of a repeated job are built once
+            rank, world = self._world()
+            p = plan(workload, params, n_paths, precision)
+            first, count = shard_range(p, rank, world)
+            lib = self.engine._lib
+            fn = {"vanilla": lib.mcb200_vanilla_launch, "basket": lib.mcb200_basket_launch, "cva": lib.mcb200_cva_launch}[workload]
+            self._job_key, self._job = key, (p, first, count, fn, params._c(), params)
+        p, first, count, fn, c_params, _ = self._job
         with torch.cuda.device(self.device):
-            self.acc.zero_()
+            self.slot = (self.slot + 1) % self.RING
+            if self.slot == 0:
+                self.ring.zero_()
+            self.acc = self.ring[self.slot]
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            _launch(self.engine, workload, p, params, seed, first, count, self.acc, stream)
+            _lib.check(fn(self.engine.handle, C.byref(p), C.byref(c_params), seed, first, count,
+                          C.c_void_p(self.acc.data_ptr()), C.c_void_p(stream)), self.engine.handle)
             combine_accumulators(self.acc, self.group)
         return p
 

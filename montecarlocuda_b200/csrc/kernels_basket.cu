@@ -11,6 +11,7 @@
 // g[], bt[], s[] with runtime bounds, which puts them in local memory (LDL/STL),
 // and multiplies the zero upper triangle too.  kFull keeps that behaviour for a caller whose p
 // is not triangular.
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -88,12 +89,18 @@ template <> struct NormalsPerBlock<double> { static constexpr int value = 2; };
 template <typename Real, int N, bool kFull>
 struct BasketTable {
     static constexpr bool kPaired = sizeof(Real) == 4 && N % 2 == 0;
+    // wide fp32 factors are read from a shared-memory copy with 16-byte loads (see Basket::column):
+    // their columns start on 16-byte boundaries
+    static constexpr bool kSharedFactor = kPaired && N >= 32;
     static __host__ __device__ constexpr int first_row(int col) { return kFull ? 0 : (kPaired ? (col & ~1) : col); }
     static __host__ __device__ constexpr int column_start(int col)
     {
         int off = 0;
-        for (int c = 0; c < col; c++)
+        for (int c = 0; c < col; c++) {
             off += N - first_row(c);
+            if (kSharedFactor)
+                off = (off + 3) & ~3;
+        }
         return off;
     }
     static constexpr int kFactor = column_start(N);
@@ -112,6 +119,40 @@ constexpr int basket_min_blocks(int n, int real_bytes)
     return blocks < 1 ? 1 : (blocks > 4 ? 4 : blocks);
 }
 
+// Shared-memory copy of a wide fp32 factor.  Read through the constant bank, a 64-asset factor
+// (8.4 KB) misses the small first-level constant cache on every access: the ncu source page of
+// profiles/r01d_basket64_f32_ffma2.txt charges a third of all warp-stall samples to FFMA2s waiting on
+// their LDCU.128 (short scoreboard).  Shared memory answers a broadcast 16-byte load in ~30 cycles.
+template <int kFloats>
+struct SharedFactor : NoShared {
+    __align__(16) float factor[kFloats];
+    __device__ __forceinline__ void load()
+    {
+        const float *src = reinterpret_cast<const float *>(mcb_basket_table);
+        for (int i = threadIdx.x; i < kFloats; i += blockDim.x)
+            factor[i] = src[i];
+    }
+};
+
+// x2a, x2b += {4 consecutive factor entries at smem address base + kByteOffset} * {z, z}
+template <int kByteOffset>
+__device__ __forceinline__ void packed_fma_quad(unsigned long long &x2a, unsigned long long &x2b, unsigned long long zz,
+                                                uint32_t base)
+{
+    asm volatile(
+        "{\n\t.reg .b64 fa, fb;\n\tld.shared.v2.b64 {fa, fb}, [%3+%4];\n\t"
+        "fma.rn.f32x2 %0, fa, %2, %0;\n\tfma.rn.f32x2 %1, fb, %2, %1;\n\t}"
+        : "+l"(x2a), "+l"(x2b)
+        : "l"(zz), "r"(base), "n"(kByteOffset));
+}
+template <int kByteOffset>
+__device__ __forceinline__ void packed_fma_pair(unsigned long long &x2, unsigned long long zz, uint32_t base)
+{
+    asm volatile("{\n\t.reg .b64 fa;\n\tld.shared.b64 fa, [%2+%3];\n\tfma.rn.f32x2 %0, fa, %1, %0;\n\t}"
+                 : "+l"(x2)
+                 : "l"(zz), "r"(base), "n"(kByteOffset));
+}
+
 template <typename RealT, int N, bool kFull>
 struct Basket {
     using Real = RealT;
@@ -124,7 +165,8 @@ struct Basket {
     struct Params {
         PhiloxKeys keys;
     };
-    using Shared = typename SharedFor<Real>::type;
+    static constexpr bool kSharedFactor = Table::kSharedFactor;
+    using Shared = std::conditional_t<kSharedFactor, SharedFactor<(kSharedFactor ? Table::kFactor : 1)>, typename SharedFor<Real>::type>;
     static __device__ __forceinline__ float grow(float x, const NoShared &) { return mufu_ex2(x); }
     static __device__ __forceinline__ double grow(double x, const SharedTables64 &sh) { return exp_tab(x, sh.t); }
     static constexpr int kBlocks = (N + kNpb - 1) / kNpb;
@@ -141,11 +183,26 @@ struct Basket {
     };
 
     // column J of the sweep: x[row] += F[row][J] * z for row = first_row(J) .. N-1
+    template <int J, int kFirst, int... kQuad>
+    static __device__ __forceinline__ void column_shared(State &st, unsigned long long zz, uint32_t base,
+                                                         std::integer_sequence<int, kQuad...>)
+    {
+        (packed_fma_quad<Table::index(J, kFirst + 4 * kQuad) * 4>(st.x2[kFirst / 2 + 2 * kQuad], st.x2[kFirst / 2 + 2 * kQuad + 1], zz,
+                                                                  base),
+         ...);
+    }
     template <int J, int... kRow>
-    static __device__ __forceinline__ void column(State &st, Real z, std::integer_sequence<int, kRow...>)
+    static __device__ __forceinline__ void column(State &st, Real z, const Shared &sh, std::integer_sequence<int, kRow...>)
     {
         constexpr int first = Table::first_row(J);
-        if constexpr (kPaired) {
+        if constexpr (kSharedFactor) {
+            constexpr int pairs = sizeof...(kRow);
+            const unsigned long long zz = pack2(z, z);
+            const uint32_t base = (uint32_t)__cvta_generic_to_shared(sh.factor);
+            column_shared<J, first>(st, zz, base, std::make_integer_sequence<int, pairs / 2>{});
+            if constexpr (pairs % 2 == 1)
+                packed_fma_pair<Table::index(J, first + 2 * (pairs - 1)) * 4>(st.x2[first / 2 + pairs - 1], zz, base);
+        } else if constexpr (kPaired) {
             // (a deeper software pipeline of the table loads was tried: ptxas re-sinks every LDCU.128
             // next to its two FFMA2s whatever the source order, it keeps two uniform quads in flight)
             const unsigned long long zz = pack2(z, z);
@@ -158,11 +215,11 @@ struct Basket {
         }
     }
     template <int J>
-    static __device__ __forceinline__ void column_if(State &st, Real z)
+    static __device__ __forceinline__ void column_if(State &st, Real z, const Shared &sh)
     {
         if constexpr (J < N) {
             constexpr int rows = N - Table::first_row(J);
-            column<J>(st, z, std::make_integer_sequence<int, (kPaired ? rows / 2 : rows)>{});
+            column<J>(st, z, sh, std::make_integer_sequence<int, (kPaired ? rows / 2 : rows)>{});
         }
     }
     // draw block JB: one Philox block -> kNpb normals -> kNpb columns
@@ -174,11 +231,11 @@ struct Basket {
         philox4x32_10(path_lo, path_hi, (uint32_t)JB, kTagBasket, P.keys, w);
         Real z[kNpb];
         normals_from_words(w, z, sh);
-        column_if<JB * kNpb + 0>(st, z[0]);
-        column_if<JB * kNpb + 1>(st, z[1]);
+        column_if<JB * kNpb + 0>(st, z[0], sh);
+        column_if<JB * kNpb + 1>(st, z[1], sh);
         if constexpr (kNpb == 4) {
-            column_if<JB * kNpb + 2>(st, z[2]);
-            column_if<JB * kNpb + 3>(st, z[3]);
+            column_if<JB * kNpb + 2>(st, z[2], sh);
+            column_if<JB * kNpb + 3>(st, z[3], sh);
         }
     }
     template <int... kJB>

@@ -153,7 +153,7 @@ int mcb200_finalize(const mcb200_plan_t *plan, const uint64_t acc[MCB200_ACC_WOR
 /* ---- per-path values (parity instrumentation; same device code as the pricing kernels) ----
  * out_host receives n_paths values of the working precision (float or double): the undiscounted
  * payoff (vanilla, basket) or the path CVA.  first_path must be a multiple of the draw-unit size
- * (4 for vanilla F32, 2 for vanilla F64, 1 otherwise). */
+ * (4 for vanilla, 1 otherwise). */
 int mcb200_vanilla_paths(mcb200_ctx *ctx, int precision, const mcb200_option_t *opt, uint64_t seed,
                          uint64_t first_path, uint64_t n_paths, void *out_host);
 int mcb200_basket_paths(mcb200_ctx *ctx, int precision, const mcb200_basket_t *opt, uint64_t seed,
@@ -161,7 +161,7 @@ int mcb200_basket_paths(mcb200_ctx *ctx, int precision, const mcb200_basket_t *o
 int mcb200_cva_paths(mcb200_ctx *ctx, int precision, const mcb200_cva_t *cva, uint64_t seed,
                      uint64_t first_path, uint64_t n_paths, void *out_host);
 /* raw generator output: n counters (4 words each) under one key -> 4 words each, and the
- * normals made from them (4 floats or 2 doubles per counter) */
+ * normals made from them (4 floats or 4 doubles per counter) */
 int mcb200_debug_philox(mcb200_ctx *ctx, uint64_t n, const uint32_t *ctr_host, const uint32_t key[2],
                         uint32_t *out_host);
 int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint32_t *ctr_host,

@@ -97,25 +97,32 @@ __device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float
 }
 
 // ---- fp64 ----
-// 52 random bits under the exponent of 1.0: f in [1, 2) exactly (one LOP3 + register pairing)
-__device__ __forceinline__ double stuffed_unit_f64(uint32_t w_hi, uint32_t w_lo)
+// One Philox block (128 bits) serves TWO fp64 Box-Muller pairs, i.e. four normals, like fp32.
+// Each pair takes 64 bits (wa, wb): the radius uniform gets 44 of them (wa and the top 12 bits of wb,
+// stuffed under the exponent of 1.0: f in [1,2), u = 2 - f in (0,1], tails to 7.8 sigma), the angle
+// the other 20 (a turn fraction k / 2^20: 2^20 directions; for anything smooth in the pair the
+// lattice error is that of a trapezoid rule on a periodic function, i.e. far below fp64 rounding).
+// The first version spent a whole block per pair (52-bit radius and angle): twice the IMAD.WIDE
+// work for bits no estimate can see.  All arithmetic after the bits is fp64: 12 + 7 + 19 + 2 = 40
+// fp64 instructions per pair on the hand-built functions of device_math64.cuh (libdevice: 68+).
+__device__ __forceinline__ void box_muller_f64(uint32_t wa, uint32_t wb, double &z0, double &z1, const Tables64 &T)
 {
-    return __hiloint2double((int)(0x3ff00000u | (w_hi & 0xfffffu)), (int)w_lo);
+    const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
+    const double r = sqrt_pos(fabs(neg2log_unit(2.0 - f, T)));
+    double cs, sn;
+    sincos_turn(wb & 0x000fffffu, 0u, cs, sn);
+    z0 = r * cs;
+    z1 = r * sn;
 }
 
-// Four words -> one fp64 Box-Muller pair (true 52-bit uniforms; the reference's "double" normals
-// are float): radius from (w0, w1), angle k / 2^52 turns from (w2, w3).
-// 9 + 7 + 18 + 3 = 37 fp64 instructions per pair on the hand-built functions of device_math64.cuh
-// (libdevice log + sqrt + sincospi: 68).
-__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], double (&z)[2], const SharedTables64 &sh)
+__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], double (&z)[4], const SharedTables64 &sh)
 {
-    const double u = 2.0 - stuffed_unit_f64(w[0], w[1]);
-    const double r = sqrt_pos(fabs(neg2log_unit(u, sh.t)));
-    double cs, sn;
-    sincos_turn(w[2], w[3], cs, sn);
-    z[0] = r * cs;
-    z[1] = r * sn;
+    box_muller_f64(w[0], w[1], z[0], z[1], sh.t);
+    box_muller_f64(w[2], w[3], z[2], z[3], sh.t);
 }
+
+// normals per Philox block, both precisions
+constexpr int kNormalsPerBlock = 4;
 
 // max(x, 0): FMNMX for fp32; for fp64 an integer mask (fmax(double) is DSETP + selects + NaN fix-up)
 __device__ __forceinline__ float positive_part(float x) { return fmaxf(x, 0.0f); }

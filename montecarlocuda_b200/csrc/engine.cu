@@ -125,7 +125,7 @@ int fill_plan(int workload, int precision, uint64_t n_paths, double scale_ref, d
     plan->workload = workload;
     plan->precision = precision;
     plan->total_paths = n_paths;
-    plan->unit_paths = workload == MCB200_VANILLA ? (precision == MCB200_F64 ? 2 : 4) : 1;
+    plan->unit_paths = workload == MCB200_VANILLA ? 4 : 1;  // one Philox block = four normals
     plan->total_units = (n_paths + plan->unit_paths - 1) / plan->unit_paths;
     plan->rounds = chunk_rounds(plan->total_units);
     plan->chunk_units = (uint64_t)kThreads * plan->rounds;
@@ -827,7 +827,8 @@ int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint3
     uint32_t *d_ctr = nullptr;
     void *d_out = nullptr;
     MCB_CUDA(ctx, cudaMalloc(&d_ctr, n * 16));
-    cudaError_t e = cudaMalloc(&d_out, n * 16);  // 4 floats or 2 doubles per counter
+    const size_t out_bytes = n * 4 * (precision == MCB200_F64 ? 8 : 4);  // 4 normals per counter
+    cudaError_t e = cudaMalloc(&d_out, out_bytes);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(d_ctr, ctr_host, n * 16, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
@@ -835,7 +836,7 @@ int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint3
                           ctx->stream);
     if (e == cudaSuccess) {
         ctx->launches++;
-        e = cudaMemcpyAsync(out_host, d_out, n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
     }
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(ctx->stream);

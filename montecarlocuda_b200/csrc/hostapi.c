@@ -35,14 +35,13 @@
 #define R_LOG logf
 #define R_SQRT sqrtf
 #define R_FABS fabsf
-#define NORMALS_PER_BLOCK 4
 #else
 #define R_EXP exp
 #define R_LOG log
 #define R_SQRT sqrt
 #define R_FABS fabs
-#define NORMALS_PER_BLOCK 2
 #endif
+#define NORMALS_PER_BLOCK 4 /* one Philox block = two Box-Muller pairs, both precisions */
 
 /* ---- printing (MonteCarloHost.c:20-65): same fields, same order ---- */
 void printVect(mc_real *mat, int c)
@@ -206,15 +205,16 @@ static void normals(const uint32_t w[4], mc_real z[NORMALS_PER_BLOCK])
         z[2 * i + 1] = rad * sinf(ang);
     }
 #else
-    uint64_t b0 = ((uint64_t)(0x3ff00000u | (w[0] & 0xfffffu)) << 32) | w[1];
-    uint64_t b1 = ((uint64_t)(0x3ff00000u | (w[2] & 0xfffffu)) << 32) | w[3];
-    double f0, f1;
-    memcpy(&f0, &b0, 8);
-    memcpy(&f1, &b1, 8);
-    const double rad = sqrt(-2.0 * log(2.0 - f0));
-    const double ang = 6.283185307179586476925286766559 * (f1 - 1.0);
-    z[0] = rad * cos(ang);
-    z[1] = rad * sin(ang);
+    for (int i = 0; i < 2; i++) {
+        const uint32_t wa = w[2 * i], wb = w[2 * i + 1];
+        const uint64_t bits = ((uint64_t)(0x3ff00000u | (wa >> 12)) << 32) | (uint32_t)((wa << 20) | ((wb >> 12) & 0x000fff00u));
+        double f;
+        memcpy(&f, &bits, 8);
+        const double rad = sqrt(-2.0 * log(2.0 - f));
+        const double ang = 6.283185307179586476925286766559 * ((double)(wb & 0x000fffffu) * 0x1p-20);
+        z[2 * i] = rad * cos(ang);
+        z[2 * i + 1] = rad * sin(ang);
+    }
 #endif
 }
 

@@ -2,7 +2,7 @@
 //
 // Replaces brownianVect + basketPayoff + basketOptMonteCarlo (DP/MonteCarloKernel.cu:74-101,
 // :133-177).  One draw unit = one path; draw block j of the path's sub-stream gives normals
-// 2j, 2j+1 (fp64) or 4j .. 4j+3 (fp32).
+// 4j .. 4j+3.
 //   x_i    = a_i + sum_j F_ij z_j      F_ij = v_i sqrt(T) L_ij,  a_i = (r - v_i^2/2) T + v_i sqrt(T) d_i
 //   payoff = max(sum_i m_i e^{x_i} - K, 0),  m_i = w_i s_i      (fp32: x in log2 units, 2^x by MUFU.EX2)
 // The mat-vec is a column sweep kept in registers: normal j is produced, applied to the N - j
@@ -77,10 +77,6 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi)
 {
     return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
-
-template <typename Real> struct NormalsPerBlock;
-template <> struct NormalsPerBlock<float> { static constexpr int value = 4; };
-template <> struct NormalsPerBlock<double> { static constexpr int value = 2; };
 
 // Table layout.  Column-major; column `col` holds rows first_row(col) .. N-1.  fp32 with an even
 // width runs on packed FMAs (FFMA2, two rows per instruction), so its columns start on an even row
@@ -161,7 +157,7 @@ struct Basket {
     static constexpr int kUnitPaths = 1;
     static constexpr int kUnroll = 1;
     static constexpr int kMinBlocks = basket_min_blocks(N, (int)sizeof(Real));
-    static constexpr int kNpb = NormalsPerBlock<Real>::value;
+    static constexpr int kNpb = kNormalsPerBlock;
     struct Params {
         PhiloxKeys keys;
     };
@@ -233,10 +229,8 @@ struct Basket {
         normals_from_words(w, z, sh);
         column_if<JB * kNpb + 0>(st, z[0], sh);
         column_if<JB * kNpb + 1>(st, z[1], sh);
-        if constexpr (kNpb == 4) {
-            column_if<JB * kNpb + 2>(st, z[2], sh);
-            column_if<JB * kNpb + 3>(st, z[3], sh);
-        }
+        column_if<JB * kNpb + 2>(st, z[2], sh);
+        column_if<JB * kNpb + 3>(st, z[3], sh);
     }
     template <int... kJB>
     static __device__ __forceinline__ void sweep(const Params &P, uint32_t path_lo, uint32_t path_hi, State &st,

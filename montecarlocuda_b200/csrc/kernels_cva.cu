@@ -29,10 +29,6 @@ constexpr int kCvaMaxDates = 1024;
 __constant__ __align__(16) unsigned char c_cva_table[kCvaMaxDates * sizeof(CvaDate<double>)];
 static TableLock g_cva_lock;
 
-template <typename Real> struct NormalsPerBlock;
-template <> struct NormalsPerBlock<float> { static constexpr int value = 4; };
-template <> struct NormalsPerBlock<double> { static constexpr int value = 2; };
-
 // pdf * polynomial(k), k = 1 / (1 + 0.2316419 |d|): the upper-tail probability of |d|
 // (Abramowitz-Stegun 26.2.17, the constants of DP/MonteCarloKernel.cu:111-116)
 template <typename Real>
@@ -61,7 +57,7 @@ struct Cva {
     static constexpr int kUnitPaths = 1;
     static constexpr int kUnroll = 1;
     static constexpr int kMinBlocks = 3;
-    static constexpr int kNpb = NormalsPerBlock<Real>::value;
+    static constexpr int kNpb = kNormalsPerBlock;
     struct Params {
         PhiloxKeys keys;
         Real y0, mu_dt, sig_dt, k;

@@ -8,10 +8,6 @@ namespace mcb {
 
 constexpr uint32_t kVanillaTag = 1u;
 
-template <typename Real> struct NormalsPerBlock;
-template <> struct NormalsPerBlock<float> { static constexpr int value = 4; };
-template <> struct NormalsPerBlock<double> { static constexpr int value = 2; };
-
 // tuned on B200 (profiles/r01_tune_vanilla.txt): CTAs per SM / unroll of the unit loop
 template <typename Real> struct VanillaTuning;
 template <> struct VanillaTuning<float> { static constexpr int kMinBlocks = 4, kUnroll = 1; };
@@ -20,7 +16,7 @@ template <> struct VanillaTuning<double> { static constexpr int kMinBlocks = 4, 
 template <typename RealT, int kMinBlocksT = VanillaTuning<RealT>::kMinBlocks, int kUnrollT = VanillaTuning<RealT>::kUnroll>
 struct Vanilla {
     using Real = RealT;
-    static constexpr int kUnitPaths = NormalsPerBlock<Real>::value;
+    static constexpr int kUnitPaths = kNormalsPerBlock;
     static constexpr int kMinBlocks = kMinBlocksT;
     static constexpr int kUnroll = kUnrollT;
     struct Params {

@@ -38,11 +38,16 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * Uniforms are built by stuffing random bits under a fixed exponent: f in [1,2) exactly,
  * u1 = 2 - f in (0,1] for the radius, f - 1 (a turn fraction) for the angle.
  * ---------------------------------------------------------------------------------------- */
-void orc_uniforms_f64(const uint32_t w[4], double f[2])
+/* fp64: a block serves two pairs; pair i = (w[2i], w[2i+1]).  f[2i] = the radius uniform's
+ * stuffed double in [1,2) (44 random bits: w[2i] and the top 12 bits of w[2i+1]), f[2i+1] = the
+ * angle as a turn fraction k / 2^20 (the low 20 bits of w[2i+1]). */
+void orc_uniforms_f64(const uint32_t w[4], double f[4])
 {
     for (int i = 0; i < 2; i++) {
-        uint64_t bits = ((uint64_t)(0x3ff00000u | (w[2 * i] & 0xfffffu)) << 32) | w[2 * i + 1];
-        memcpy(&f[i], &bits, 8);
+        uint32_t wa = w[2 * i], wb = w[2 * i + 1];
+        uint64_t bits = ((uint64_t)(0x3ff00000u | (wa >> 12)) << 32) | (uint32_t)((wa << 20) | ((wb >> 12) & 0x000fff00u));
+        memcpy(&f[2 * i], &bits, 8);
+        f[2 * i + 1] = (double)(wb & 0x000fffffu) * 0x1p-20;
     }
 }
 
@@ -54,14 +59,16 @@ void orc_uniforms_f32(const uint32_t w[4], float f[4])
     }
 }
 
-void orc_normals_f64(const uint32_t w[4], double z[2])
+void orc_normals_f64(const uint32_t w[4], double z[4])
 {
-    double f[2];
+    double f[4];
     orc_uniforms_f64(w, f);
-    double rad = sqrt(-2.0 * log(2.0 - f[0]));
-    double ang = 6.283185307179586476925286766559 * (f[1] - 1.0);
-    z[0] = rad * cos(ang);
-    z[1] = rad * sin(ang);
+    for (int i = 0; i < 2; i++) {
+        double rad = sqrt(-2.0 * log(2.0 - f[2 * i]));
+        double ang = 6.283185307179586476925286766559 * f[2 * i + 1];
+        z[2 * i] = rad * cos(ang);
+        z[2 * i + 1] = rad * sin(ang);
+    }
 }
 
 void orc_normals_f32(const uint32_t w[4], float z[4])
@@ -83,7 +90,7 @@ void orc_normals_f32(const uint32_t w[4], float z[4])
 
 #define REAL double
 #define FN(name) CAT(name, f64)
-#define NPB 2
+#define NPB 4
 #define R_EXP exp
 #define R_LOG log
 #define R_SQRT sqrt

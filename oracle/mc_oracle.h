@@ -41,11 +41,11 @@ enum { ORC_TAG_VANILLA = 1, ORC_TAG_BASKET = 2, ORC_TAG_CVA = 3 };
 enum { ORC_THREADS = 256, ORC_LANES = 5 };
 
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* four words -> two fp64 normals / four fp32 normals (Box-Muller on bit-stuffed uniforms) */
-void orc_normals_f64(const uint32_t w[4], double z[2]);
+/* four words -> four normals (two Box-Muller pairs on bit-stuffed uniforms), either precision */
+void orc_normals_f64(const uint32_t w[4], double z[4]);
 void orc_normals_f32(const uint32_t w[4], float z[4]);
 /* the exact uniform stage, for bit-exact comparison with the device */
-void orc_uniforms_f64(const uint32_t w[4], double f[2]); /* f in [1,2) */
+void orc_uniforms_f64(const uint32_t w[4], double f[4]); /* {radius f in [1,2), angle in turns} x 2 */
 void orc_uniforms_f32(const uint32_t w[4], float f[4]);
 
 /* ---- closed forms and helpers ---- */

@@ -57,7 +57,7 @@ class Oracle:
     def normals(self, words, precision="f64"):
         w = u32x4(*[int(x) for x in words])
         if precision == "f64":
-            z = (C.c_double * 2)()
+            z = (C.c_double * 4)()
             self.lib.orc_normals_f64(w, z)
             return np.array(z, dtype=np.float64)
         z = (C.c_float * 4)()
@@ -67,7 +67,7 @@ class Oracle:
     def uniforms(self, words, precision="f64"):
         w = u32x4(*[int(x) for x in words])
         if precision == "f64":
-            z = (C.c_double * 2)()
+            z = (C.c_double * 4)()
             self.lib.orc_uniforms_f64(w, z)
             return np.array(z, dtype=np.float64)
         z = (C.c_float * 4)()

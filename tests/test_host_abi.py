@@ -69,7 +69,7 @@ def test_plan_geometry(ensure_built, oracle):
     assert (p.unit_paths, p.rounds, p.chunk_units, p.n_chunks) == (4, 64, 16384, 65536)
     assert (p.scale_exp_sum, p.scale_exp_sumsq) == (73, 66) and p.discount == pytest.approx(np.exp(-0.05))
     p = m.plan("vanilla", opt, 1 << 32, "f64")
-    assert (p.unit_paths, p.rounds, p.n_chunks) == (2, 64, 131072)
+    assert (p.unit_paths, p.rounds, p.chunk_units, p.n_chunks) == (4, 64, 16384, 65536)
     cva = m.CVA(0.03, 0.6, opt, 50)
     p = m.plan("cva", cva, 1 << 26, "f64")
     assert (p.unit_paths, p.rounds, p.n_chunks, p.discount) == (1, 4, 65536, 1.0)

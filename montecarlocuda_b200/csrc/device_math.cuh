@@ -28,6 +28,12 @@ struct SharedTables64 {
             t.log_tab[i][1] = kLogTable[i][1];
             t.exp_tab[i] = kExpTable[i];
         }
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            t.turn_hi[i][0] = kTurnHiTable[i][0];
+            t.turn_hi[i][1] = kTurnHiTable[i][1];
+            t.turn_lo[i][0] = kTurnLoTable[i][0];
+            t.turn_lo[i][1] = kTurnLoTable[i][1];
+        }
     }
 };
 template <typename Real> struct SharedFor;
@@ -103,14 +109,14 @@ __device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float
 // the other 20 (a turn fraction k / 2^20: 2^20 directions; for anything smooth in the pair the
 // lattice error is that of a trapezoid rule on a periodic function, i.e. far below fp64 rounding).
 // The first version spent a whole block per pair (52-bit radius and angle): twice the IMAD.WIDE
-// work for bits no estimate can see.  All arithmetic after the bits is fp64: 12 + 7 + 19 + 2 = 40
-// fp64 instructions per pair on the hand-built functions of device_math64.cuh (libdevice: 68+).
+// work for bits no estimate can see.  All arithmetic after the bits is fp64: 12 (log) + 7 (sqrt) +
+// 4 (cos/sin from the two-level table) + 2 = 25 fp64 instructions per pair (libdevice: 68+).
 __device__ __forceinline__ void box_muller_f64(uint32_t wa, uint32_t wb, double &z0, double &z1, const Tables64 &T)
 {
     const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
     const double r = sqrt_pos(fabs(neg2log_unit(2.0 - f, T)));
     double cs, sn;
-    sincos_turn(wb & 0x000fffffu, 0u, cs, sn);
+    sincos_turn20(wb & 0x000fffffu, cs, sn, T);
     z0 = r * cs;
     z1 = r * sn;
 }

@@ -109,8 +109,8 @@ struct BasketTable {
 
 constexpr int basket_min_blocks(int n, int real_bytes)
 {
-    // registers: the accumulators + ~44 for generator, normals and loop state
-    const int regs = n * real_bytes / 4 + 44;
+    // registers: the accumulators + ~44 (fp32) / ~60 (fp64) for generator, normals and loop state
+    const int regs = n * real_bytes / 4 + (real_bytes == 8 ? 60 : 44);
     const int blocks = 65536 / (kThreads * regs);
     return blocks < 1 ? 1 : (blocks > 4 ? 4 : blocks);
 }

@@ -76,7 +76,8 @@ debug_reduce_kernel(const double *__restrict__ values, unsigned long long n_vali
 }
 
 // The fp64 special functions on their own: fn 0 = -2 ln(u), 1 = sqrt, 2 = 1/x, 3 = e^x,
-// 4 = cos/sin of 2 pi k / 2^52 (input reinterpreted as the 52-bit integer k; two outputs).
+// 4 = cos/sin of 2 pi k / 2^52 (input reinterpreted as the 52-bit integer k; two outputs),
+// 5 = cos/sin of 2 pi k / 2^20 from the two-level table (k = low word of the input).
 __global__ void debug_math64_kernel(int fn, unsigned long long n, const double *__restrict__ in,
                                     double *__restrict__ out)
 {
@@ -92,7 +93,8 @@ __global__ void debug_math64_kernel(int fn, unsigned long long n, const double *
             case 1: a = sqrt_pos(x); break;
             case 2: a = rcp_newton(x); break;
             case 3: a = exp_tab(x, sh.t); break;
-            default: sincos_turn((uint32_t)__double2hiint(x), (uint32_t)__double2loint(x), a, b); break;
+            case 4: sincos_turn((uint32_t)__double2hiint(x), (uint32_t)__double2loint(x), a, b); break;
+            default: sincos_turn20((uint32_t)__double2loint(x), a, b, sh.t); break;
         }
         out[2 * i] = a;
         out[2 * i + 1] = b;

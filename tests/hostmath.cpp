@@ -13,12 +13,18 @@ static const Tables64 &tables()
     if (!g_ready) {
         std::memcpy(g_tables.log_tab, kLogTable, sizeof kLogTable);
         std::memcpy(g_tables.exp_tab, kExpTable, sizeof kExpTable);
+        std::memcpy(g_tables.turn_hi, kTurnHiTable, sizeof kTurnHiTable);
+        std::memcpy(g_tables.turn_lo, kTurnLoTable, sizeof kTurnLoTable);
         g_ready = true;
     }
     return g_tables;
 }
 
 extern "C" {
+void hm_sincos20(const uint32_t *k, double *cs, double *sn, long n)
+{
+    for (long i = 0; i < n; i++) sincos_turn20(k[i], cs[i], sn[i], tables());
+}
 void hm_neg2log(const double *u, double *out, long n) { for (long i = 0; i < n; i++) out[i] = neg2log_unit(u[i], tables()); }
 void hm_sqrt(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = sqrt_pos(x[i]); }
 void hm_rcp(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = rcp_newton(x[i]); }

@@ -54,6 +54,11 @@ def check(run):
     ang = 2 * np.longdouble("3.14159265358979323846264338327950288") * (k.astype(np.longdouble) * np.longdouble(2.0) ** -52)
     assert np.abs(out[:, 0] - np.cos(ang).astype(np.float64)).max() <= 3e-16
     assert np.abs(out[:, 1] - np.sin(ang).astype(np.float64)).max() <= 3e-16
+    k20 = np.concatenate([np.arange(0, 1 << 20, 37, dtype=np.uint64), np.array([0, 1, 1023, 1024, (1 << 20) - 1, 1 << 19, 3 << 18], dtype=np.uint64)])
+    out = run(5, k20.view(np.float64))
+    ang = 2 * np.longdouble("3.14159265358979323846264338327950288") * (k20.astype(np.longdouble) * np.longdouble(2.0) ** -20)
+    assert np.abs(out[:, 0] - np.cos(ang).astype(np.float64)).max() <= 3e-16      # two-level table: four rounded entries
+    assert np.abs(out[:, 1] - np.sin(ang).astype(np.float64)).max() <= 3e-16
 
 
 @pytest.fixture(scope="module")
@@ -70,7 +75,12 @@ def test_host_build_of_device_math(hostmath):
     def run(fn, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         out = np.zeros((len(x), 2))
-        if fn == 4:
+        if fn == 5:
+            k = np.ascontiguousarray(x.view(np.uint64) & np.uint64(0xFFFFFFFF), dtype=np.uint64).astype(np.uint32)
+            cs, sn = np.empty(len(x)), np.empty(len(x))
+            hostmath.hm_sincos20(C.c_void_p(k.ctypes.data), C.c_void_p(cs.ctypes.data), C.c_void_p(sn.ctypes.data), C.c_long(len(x)))
+            out[:, 0], out[:, 1] = cs, sn
+        elif fn == 4:
             k = x.view(np.uint64)
             hi = (k >> np.uint64(32)).astype(np.uint32)
             lo = (k & np.uint64(0xFFFFFFFF)).astype(np.uint32)

@@ -127,6 +127,20 @@ int mcb200_basket_multi(mcb200_ctx **ctxs, int n_ctx, int precision, const mcb20
 int mcb200_cva_multi(mcb200_ctx **ctxs, int n_ctx, int precision, const mcb200_cva_t *cva,
                      uint64_t n_paths, uint64_t seed, mcb200_result_t *out);
 
+/* ---- batched pricing: many jobs, one synchronisation ----
+ * replaces the serial sweep of the reference's cvaOpt driver (double_precision/cvaOpt.cu:70-109: one
+ * blocking dev_cvaEquityOption call per grid size and thread count).  params points to the
+ * mcb200_option_t / mcb200_basket_t / mcb200_cva_t of the job's workload.  out[i] is exactly what the
+ * one-call entry point returns for job i (kernel_ms = device time of the whole batch); status_out
+ * (optional, n_jobs entries) receives the per-job status, the return value the first failure. */
+typedef struct {
+    int workload, precision;
+    const void *params;
+    uint64_t n_paths, seed;
+} mcb200_job_t;
+int mcb200_price_batch(mcb200_ctx *ctx, int n_jobs, const mcb200_job_t *jobs, mcb200_result_t *out,
+                       int *status_out);
+
 /* ---- sharded pricing (one process per GPU; the combine is the caller's all-reduce) ----
  * plan -> shard range for (rank, world) -> asynchronous launch accumulating into a DEVICE
  * accumulator block (MCB200_ACC_WORDS zero-initialised 64-bit words owned by the caller) on the

@@ -44,6 +44,11 @@ class ResultT(C.Structure):
         "sum", "sumsq", "mean", "expected", "confidence", "std_error", "kernel_ms")]
 
 
+class JobT(C.Structure):
+    """mcb200_job_t: one job of mcb200_price_batch"""
+    _fields_ = [("workload", C.c_int), ("precision", C.c_int), ("params", C.c_void_p), ("n_paths", C.c_uint64), ("seed", C.c_uint64)]
+
+
 class PlanT(C.Structure):
     _fields_ = [("workload", C.c_int), ("precision", C.c_int), ("total_paths", C.c_uint64),
                 ("unit_paths", C.c_int), ("rounds", C.c_int), ("total_units", C.c_uint64),
@@ -68,6 +73,7 @@ _SIGNATURES = {
     "mcb200_vanilla_multi": (C.c_int, [_P(_CTX), C.c_int, C.c_int, _P(OptionT), C.c_uint64, C.c_uint64, _P(ResultT)]),
     "mcb200_basket_multi": (C.c_int, [_P(_CTX), C.c_int, C.c_int, _P(BasketT), C.c_uint64, C.c_uint64, _P(ResultT)]),
     "mcb200_cva_multi": (C.c_int, [_P(_CTX), C.c_int, C.c_int, _P(CvaT), C.c_uint64, C.c_uint64, _P(ResultT)]),
+    "mcb200_price_batch": (C.c_int, [_CTX, C.c_int, _P(JobT), _P(ResultT), _P(C.c_int)]),
     "mcb200_plan_vanilla": (C.c_int, [C.c_int, _P(OptionT), C.c_uint64, _P(PlanT)]),
     "mcb200_plan_basket": (C.c_int, [C.c_int, _P(BasketT), C.c_uint64, _P(PlanT)]),
     "mcb200_plan_cva": (C.c_int, [C.c_int, _P(CvaT), C.c_uint64, _P(PlanT)]),

@@ -155,6 +155,20 @@ class Engine:
         _lib.check(self._lib.mcb200_cva(self._ctx, _prec(precision), C.byref(c), n_paths, seed, C.byref(r)), self._ctx)
         return OptionValue._from(r)
 
+    def price_batch(self, jobs, seed: int = DEFAULT_SEED):
+        """Price many jobs with one synchronisation.  jobs: iterable of (workload, params, n_paths, precision)
+        with workload in {"vanilla", "basket", "cva"}.  Returns a list of OptionValue, in order."""
+        jobs = list(jobs)
+        codes = {"vanilla": _lib.VANILLA, "basket": _lib.BASKET, "cva": _lib.CVA}
+        c_params = [params._c() for _, params, _, _ in jobs]          # keep the C structs alive
+        arr = (_lib.JobT * len(jobs))()
+        for i, (workload, _, n_paths, precision) in enumerate(jobs):
+            arr[i] = _lib.JobT(codes[workload], _prec(precision), C.cast(C.pointer(c_params[i]), C.c_void_p), n_paths, seed)
+        out = (_lib.ResultT * len(jobs))()
+        status = (C.c_int * len(jobs))()
+        _lib.check(self._lib.mcb200_price_batch(self._ctx, len(jobs), arr, out, status), self._ctx)
+        return [OptionValue._from(r) for r in out]
+
     # ---- per-path values (parity instrumentation) ----
     def _paths(self, fn, c_struct, precision, seed, first_path, n_paths) -> np.ndarray:
         p = _prec(precision)

@@ -28,6 +28,9 @@ struct mcb200_ctx {
     cudaStream_t stream = nullptr;
     unsigned long long *d_acc = nullptr;
     unsigned long long *h_acc = nullptr;  // pinned
+    // accumulators of a batch (mcb200_price_batch): grown on demand, kept for the context's life
+    unsigned long long *d_batch = nullptr, *h_batch = nullptr;
+    size_t batch_capacity = 0;  // in jobs
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::string last_error;
     uint64_t launches = 0;
@@ -517,6 +520,10 @@ int mcb200_destroy(mcb200_ctx *ctx)
             cudaFree(ctx->d_acc);
         if (ctx->h_acc)
             cudaFreeHost(ctx->h_acc);
+        if (ctx->d_batch)
+            cudaFree(ctx->d_batch);
+        if (ctx->h_batch)
+            cudaFreeHost(ctx->h_batch);
         if (ctx->stream)
             cudaStreamDestroy(ctx->stream);
         cudaGetLastError();
@@ -742,6 +749,85 @@ int mcb200_cva(mcb200_ctx *ctx, int precision, const mcb200_cva_t *cva, uint64_t
                mcb200_result_t *out)
 {
     return mcb200_cva_multi(&ctx, 1, precision, cva, n_paths, seed, out);
+}
+
+// ---- batched pricing: many jobs, one synchronisation ----
+// The reference's cvaOpt driver prices 5 grids x 4 thread counts one blocking call at a time, each
+// with its own allocations, XORWOW seeding and device-to-host copy (double_precision/cvaOpt.cu:70-109).
+// Here every job is enqueued on the context's stream into its own accumulator block, and the host
+// waits and reads back ONCE; a job's result is exactly what the one-call API returns for it.
+int mcb200_price_batch(mcb200_ctx *ctx, int n_jobs, const mcb200_job_t *jobs, mcb200_result_t *out, int *status_out)
+{
+    if (!ctx || n_jobs < 1 || !jobs || !out)
+        return MCB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    if ((size_t)n_jobs > ctx->batch_capacity) {
+        if (ctx->d_batch)
+            cudaFree(ctx->d_batch);
+        if (ctx->h_batch)
+            cudaFreeHost(ctx->h_batch);
+        ctx->d_batch = ctx->h_batch = nullptr;
+        ctx->batch_capacity = 0;
+        const size_t bytes = sizeof(unsigned long long) * kAccWords * (size_t)n_jobs;
+        MCB_CUDA(ctx, cudaMalloc(&ctx->d_batch, bytes));
+        MCB_CUDA(ctx, cudaMallocHost(&ctx->h_batch, bytes));
+        ctx->batch_capacity = (size_t)n_jobs;
+    }
+    const size_t bytes = sizeof(unsigned long long) * kAccWords * (size_t)n_jobs;
+    std::vector<mcb200_plan_t> plans((size_t)n_jobs);
+    std::vector<int> status((size_t)n_jobs, MCB200_OK);
+    MCB_CUDA(ctx, cudaMemsetAsync(ctx->d_batch, 0, bytes, ctx->stream));
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+    for (int i = 0; i < n_jobs; i++) {
+        const mcb200_job_t &j = jobs[i];
+        AnyJob job;
+        int st = MCB200_ERR_INVALID;
+        if (j.params) {
+            switch (j.workload) {
+                case MCB200_VANILLA:
+                    st = mcb200_plan_vanilla(j.precision, (const mcb200_option_t *)j.params, j.n_paths, &plans[i]);
+                    if (st == MCB200_OK)
+                        st = make_vanilla_job(j.precision, (const mcb200_option_t *)j.params, j.seed, &job.vanilla);
+                    break;
+                case MCB200_BASKET:
+                    st = mcb200_plan_basket(j.precision, (const mcb200_basket_t *)j.params, j.n_paths, &plans[i]);
+                    if (st == MCB200_OK)
+                        st = make_basket_job((const mcb200_basket_t *)j.params, j.seed, &job.basket);
+                    break;
+                case MCB200_CVA:
+                    st = mcb200_plan_cva(j.precision, (const mcb200_cva_t *)j.params, j.n_paths, &plans[i]);
+                    if (st == MCB200_OK)
+                        st = make_cva_job(j.precision, (const mcb200_cva_t *)j.params, j.seed, &job.cva);
+                    break;
+                default: break;
+            }
+        }
+        if (st == MCB200_OK)
+            st = enqueue(ctx, plans[i], job, 0, plans[i].n_chunks, ctx->d_batch + (size_t)i * kAccWords, ctx->stream);
+        status[i] = st;
+    }
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+    MCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_batch, ctx->d_batch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    MCB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    int worst = MCB200_OK;
+    for (int i = 0; i < n_jobs; i++) {
+        std::memset(&out[i], 0, sizeof out[i]);
+        if (status[i] == MCB200_OK) {
+            status[i] = mcb200_finalize(&plans[i], (const uint64_t *)(ctx->h_batch + (size_t)i * kAccWords), &out[i]);
+            out[i].kernel_ms = ms;  // device time of the whole batch
+        }
+        if (status_out)
+            status_out[i] = status[i];
+        if (status[i] != MCB200_OK && worst == MCB200_OK)
+            worst = status[i];
+    }
+    if (worst != MCB200_OK)
+        return fail(ctx, worst, "at least one job of the batch failed; see the per-job status");
+    return MCB200_OK;
 }
 
 // ---- per-path values ----

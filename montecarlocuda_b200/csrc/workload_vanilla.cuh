@@ -10,8 +10,8 @@ constexpr uint32_t kVanillaTag = 1u;
 
 // tuned on B200 (profiles/r01_tune_vanilla.txt): CTAs per SM / unroll of the unit loop
 template <typename Real> struct VanillaTuning;
-template <> struct VanillaTuning<float> { static constexpr int kMinBlocks = 4, kUnroll = 1; };
-template <> struct VanillaTuning<double> { static constexpr int kMinBlocks = 4, kUnroll = 1; };
+template <> struct VanillaTuning<float> { static constexpr int kMinBlocks = 8, kUnroll = 1; };
+template <> struct VanillaTuning<double> { static constexpr int kMinBlocks = 3, kUnroll = 1; };
 
 template <typename RealT, int kMinBlocksT = VanillaTuning<RealT>::kMinBlocks, int kUnrollT = VanillaTuning<RealT>::kUnroll>
 struct Vanilla {

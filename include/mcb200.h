@@ -108,6 +108,16 @@ const char *mcb200_strerror(int status);
 const char *mcb200_last_error(const mcb200_ctx *ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t mcb200_launch_count(const mcb200_ctx *ctx);
+/* Which kernel prices a wide single-precision basket (32 < n <= 64 assets):
+ *   MCB200_BASKET_TENSOR (default)  the correlated draw L*g of brownianVect (DP/MonteCarloKernel.cu:74-87) runs on the
+ *                                   tcgen05 tensor cores as a 3xTF32 128-path tile product (csrc/basket_tc.cuh);
+ *   MCB200_BASKET_FFMA              the in-register packed-FMA column sweep used for every other width.
+ * Both consume the same Philox stream; they round the mat-vec differently, so their prices agree to fp32
+ * accuracy per path, not bit for bit.  Each is bit-reproducible across grid shapes and GPU counts.
+ * Process-wide; before the first call the environment variable MCB200_BASKET_ENGINE (0 / 1) decides. */
+enum { MCB200_BASKET_TENSOR = 0, MCB200_BASKET_FFMA = 1 };
+int mcb200_set_basket_engine(int engine);
+int mcb200_get_basket_engine(void);
 
 /* ---- one-call pricing: host structs in, host result out, synchronous ----
  * replaces dev_vanillaOpt / dev_basketOpt / dev_cvaEquityOption

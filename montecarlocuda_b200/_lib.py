@@ -67,6 +67,8 @@ _SIGNATURES = {
     "mcb200_strerror": (C.c_char_p, [C.c_int]),
     "mcb200_last_error": (C.c_char_p, [_CTX]),
     "mcb200_launch_count": (C.c_uint64, [_CTX]),
+    "mcb200_set_basket_engine": (C.c_int, [C.c_int]),
+    "mcb200_get_basket_engine": (C.c_int, []),
     "mcb200_vanilla": (C.c_int, [_CTX, C.c_int, _P(OptionT), C.c_uint64, C.c_uint64, _P(ResultT)]),
     "mcb200_basket": (C.c_int, [_CTX, C.c_int, _P(BasketT), C.c_uint64, C.c_uint64, _P(ResultT)]),
     "mcb200_cva": (C.c_int, [_CTX, C.c_int, _P(CvaT), C.c_uint64, C.c_uint64, _P(ResultT)]),

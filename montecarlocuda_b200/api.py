@@ -101,6 +101,19 @@ class OptionValue:
         return OptionValue(r.expected, r.confidence, r.std_error, int(r.n_paths), r.mean, r.sum, r.sumsq, r.kernel_ms)
 
 
+BASKET_TENSOR, BASKET_FFMA = 0, 1
+
+
+def set_basket_engine(engine: int) -> None:
+    """Process-wide: which kernel prices wide fp32 baskets (32 < n <= 64): BASKET_TENSOR (tcgen05, default)
+    or BASKET_FFMA (the packed-FMA column sweep).  Mirrors mcb200_set_basket_engine (include/mcb200.h)."""
+    _lib.check(_lib.load().mcb200_set_basket_engine(int(engine)))
+
+
+def get_basket_engine() -> int:
+    return int(_lib.load().mcb200_get_basket_engine())
+
+
 class Engine:
     """Persistent pricing context on one CUDA device (stream, accumulator, events)."""
 

@@ -537,6 +537,15 @@ int mcb200_sm_count(const mcb200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t mcb200_launch_count(const mcb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 const char *mcb200_last_error(const mcb200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 
+int mcb200_set_basket_engine(int engine)
+{
+    if (engine != MCB200_BASKET_TENSOR && engine != MCB200_BASKET_FFMA)
+        return MCB200_ERR_INVALID;
+    basket_engine_set(engine);
+    return MCB200_OK;
+}
+int mcb200_get_basket_engine(void) { return basket_engine_get(); }
+
 const char *mcb200_strerror(int status)
 {
     switch (status) {

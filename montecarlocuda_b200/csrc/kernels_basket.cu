@@ -11,6 +11,8 @@
 // g[], bt[], s[] with runtime bounds, which puts them in local memory (LDL/STL),
 // and multiplies the zero upper triangle too.  kFull keeps that behaviour for a caller whose p
 // is not triangular.
+#include <atomic>
+#include <cstdlib>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -271,6 +273,12 @@ struct Basket {
     }
 };
 
+}  // namespace mcb
+
+#include "basket_tc.cuh"
+
+namespace mcb {
+
 // Host: narrow the fp64 job into the kernel's table.  Assets beyond job.n (padding up to the
 // template width) get weight 0 and a zero factor row/column: they add exactly 0 to the payoff.
 template <typename Real, int N, bool kFull>
@@ -333,6 +341,69 @@ static int occupancy_t()
     return n;
 }
 
+// ---- tensor-core engine (basket_tc.cuh): fp32, 32 < n <= 64 ----
+static std::atomic<int> g_basket_engine{-1};  // -1: not set (environment decides), 0: auto, 1: FFMA only
+
+int basket_engine_get()
+{
+    int e = g_basket_engine.load();
+    if (e < 0) {
+        const char *env = std::getenv("MCB200_BASKET_ENGINE");
+        e = (env && (env[0] == '1' || env[0] == 'f' || env[0] == 'F')) ? 1 : 0;
+        g_basket_engine.store(e);
+    }
+    return e;
+}
+void basket_engine_set(int engine) { g_basket_engine.store(engine == 1 ? 1 : 0); }
+
+bool basket_uses_tensor_cores(int precision, int n)
+{
+    return precision == 0 && n > 32 && n <= kTcWidth && basket_engine_get() == 0;
+}
+
+static void fill_tc_table(const BasketJob &job, BasketTcTable &T)
+{
+    const double unit = 1.4426950408889634074;  // log2(e): the exponents feed MUFU.EX2
+    for (int i = 0; i < kTcWidth; i++) {
+        for (int k = 0; k < kTcWidth; k++)
+            T.f[i * kTcWidth + k] = (float)((i < job.n && k < job.n) ? job.factor[i * job.n + k] * unit : 0.0);
+        T.a[i] = (float)(i < job.n ? job.a[i] * unit : 0.0);
+        T.m[i] = (float)(i < job.n ? job.m[i] : 0.0);
+    }
+    T.k = (float)job.k;
+}
+
+template <bool kFull>
+static cudaError_t launch_tc(const BasketJob &job, const Geometry *geom, int grid, unsigned long long *d_acc,
+                             unsigned long long first_unit, unsigned long long n_units, void *d_out, cudaStream_t stream)
+{
+    static_assert(sizeof(BasketTcTable) <= kBasketTableBytes, "tensor-core basket table exceeds its constant buffer");
+    std::vector<unsigned char> staging(sizeof(BasketTcTable) + 1);
+    fill_tc_table(job, *reinterpret_cast<BasketTcTable *>(staging.data()));
+    staging[sizeof(BasketTcTable)] = 0x7c;  // layout tag: never equal to an FFMA-engine image of the same size
+    BasketTcParams p;
+    p.keys = job.keys;
+    TableUse use(g_basket_lock, stream, staging.data(), staging.size());
+    if (use.status() != cudaSuccess)
+        return use.status();
+    if (use.needs_upload()) {
+        cudaError_t e = cudaMemcpyToSymbolAsync(mcb_basket_table, staging.data(), sizeof(BasketTcTable), 0,
+                                                cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) {
+            use.invalidate();
+            return e;
+        }
+    }
+    if (geom) {
+        basket_tc_accumulate_kernel<kFull><<<grid, kThreads, 0, stream>>>(p, *geom, d_acc);
+    } else {
+        const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
+        basket_tc_paths_kernel<kFull><<<(int)(blocks < 296ull ? blocks : 296ull), kThreads, 0, stream>>>(p, first_unit, n_units,
+                                                                                                       (float *)d_out);
+    }
+    return cudaGetLastError();
+}
+
 int basket_padded_width(int n)
 {
     static const int widths[] = {3, 4, 8, 10, 16, 32, 64};
@@ -380,6 +451,9 @@ int basket_padded_width(int n)
 
 int basket_blocks_per_sm(int precision, int n, bool full)
 {
+    if (basket_uses_tensor_cores(precision, n))
+        return 2;  // 2 CTAs x 256 tensor-memory columns = all 512
+
 #define MCB_OCC(R, W, F) occupancy_t<R, W, F>()
     MCB_BASKET_DISPATCH(MCB_OCC)
 #undef MCB_OCC
@@ -391,6 +465,9 @@ cudaError_t basket_launch(int precision, const BasketJob &job, const Geometry &g
 {
     const int n = job.n;
     const bool full = job.full;
+    if (basket_uses_tensor_cores(precision, n))
+        return full ? launch_tc<true>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream)
+                    : launch_tc<false>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream);
 #define MCB_LAUNCH(R, W, F) launch_t<R, W, F>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream)
     MCB_BASKET_DISPATCH(MCB_LAUNCH)
 #undef MCB_LAUNCH
@@ -402,6 +479,9 @@ cudaError_t basket_paths(int precision, const BasketJob &job, unsigned long long
 {
     const int n = job.n;
     const bool full = job.full;
+    if (basket_uses_tensor_cores(precision, n))
+        return full ? launch_tc<true>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream)
+                    : launch_tc<false>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream);
 #define MCB_PATHS(R, W, F) launch_t<R, W, F>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream)
     MCB_BASKET_DISPATCH(MCB_PATHS)
 #undef MCB_PATHS

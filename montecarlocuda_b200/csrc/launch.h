@@ -33,6 +33,11 @@ struct BasketJob {
 };
 int basket_padded_width(int n);  // template width that serves n assets, 0 if unsupported
 int basket_blocks_per_sm(int precision, int n, bool full);
+// which kernel serves wide fp32 baskets (32 < n <= 64): 0 = tensor cores (tcgen05, basket_tc.cuh), 1 = FFMA2 only.
+// Process-wide; first read falls back to the environment variable MCB200_BASKET_ENGINE (0 / 1).
+int basket_engine_get();
+void basket_engine_set(int engine);
+bool basket_uses_tensor_cores(int precision, int n);
 cudaError_t basket_launch(int precision, const BasketJob &job, const Geometry &geom, int grid,
                           unsigned long long *d_acc, cudaStream_t stream);
 cudaError_t basket_paths(int precision, const BasketJob &job, unsigned long long first_unit,

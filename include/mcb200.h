@@ -177,7 +177,7 @@ int mcb200_finalize(const mcb200_plan_t *plan, const uint64_t acc[MCB200_ACC_WOR
 /* ---- per-path values (parity instrumentation; same device code as the pricing kernels) ----
  * out_host receives n_paths values of the working precision (float or double): the undiscounted
  * payoff (vanilla, basket) or the path CVA.  first_path must be a multiple of the draw-unit size
- * (4 for vanilla, 1 otherwise). */
+ * (vanilla: 6 in single precision, 4 in double; 1 otherwise). */
 int mcb200_vanilla_paths(mcb200_ctx *ctx, int precision, const mcb200_option_t *opt, uint64_t seed,
                          uint64_t first_path, uint64_t n_paths, void *out_host);
 int mcb200_basket_paths(mcb200_ctx *ctx, int precision, const mcb200_basket_t *opt, uint64_t seed,
@@ -185,7 +185,8 @@ int mcb200_basket_paths(mcb200_ctx *ctx, int precision, const mcb200_basket_t *o
 int mcb200_cva_paths(mcb200_ctx *ctx, int precision, const mcb200_cva_t *cva, uint64_t seed,
                      uint64_t first_path, uint64_t n_paths, void *out_host);
 /* raw generator output: n counters (4 words each) under one key -> 4 words each, and the
- * normals made from them (4 floats or 4 doubles per counter) */
+ * normals made from them (6 floats or 4 doubles per counter: one Philox block is three single-precision
+ * or two double-precision Box-Muller pairs) */
 int mcb200_debug_philox(mcb200_ctx *ctx, uint64_t n, const uint32_t *ctr_host, const uint32_t key[2],
                         uint32_t *out_host);
 int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint32_t *ctr_host,

@@ -208,7 +208,7 @@ class Engine:
     def normals(self, counters: np.ndarray, key, precision=F64) -> np.ndarray:
         p = _prec(precision)
         ctr = np.ascontiguousarray(counters, dtype=np.uint32).reshape(-1, 4)
-        out = np.empty((len(ctr), 4), dtype=np.float64 if p == F64 else np.float32)
+        out = np.empty((len(ctr), 4 if p == F64 else 6), dtype=np.float64 if p == F64 else np.float32)
         k = (C.c_uint32 * 2)(int(key[0]), int(key[1]))
         _lib.check(self._lib.mcb200_debug_normals(self._ctx, p, len(ctr), ctr.ctypes.data, k, out.ctypes.data), self._ctx)
         return out

@@ -3,7 +3,7 @@
 //
 // Same estimator as Basket<float, 64, *> (brownianVect + basketPayoff + basketOptMonteCarlo,
 // DP/MonteCarloKernel.cu:74-101, :133-177) and the same Philox stream: draw block j of a path's
-// sub-stream gives normals 4j .. 4j+3.  What changes is who multiplies by the factor.  On the FFMA
+// sub-stream gives normals 6j .. 6j+5.  What changes is who multiplies by the factor.  On the FFMA
 // path the triangular mat-vec is 1056 FFMA2 + 565 LDS.128 of the 3144 instructions of a path
 // (profiles/r01f_basket64_f32_smem.txt): over a tile of 128 paths it is the dense contraction
 //     X[128 paths x 64 assets] = Z[128 x 64 normals] * F^T,      F = diag(v sqrt(T)) L  (log2 units)
@@ -224,31 +224,64 @@ __device__ __forceinline__ void basket_tc_teardown(BasketTcShared &sh)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "n"(256) : "memory");
 }
 
-// One K half: 32 normals of this thread's path -> A buffer, then the tile's 12 MMAs.
-template <int kHalf, bool kFull>
-__device__ __forceinline__ void basket_tc_half(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, BasketTcTile &t)
+// 16 normals -> exact hi / lo split -> 16 columns of the A_hi and A_lo buffers of this thread's lane
+__device__ __forceinline__ void basket_tc_store16(const float *z, uint32_t lane_d, int col)
 {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t h = __float_as_uint(z[i]) & 0xffffe000u;
+        hi[i] = h;
+        lo[i] = __float_as_uint(z[i] - __uint_as_float(h));
+    }
+    tc::st16(lane_d + 64 + col, hi);
+    tc::st16(lane_d + 96 + col, lo);
+}
+
+// One K half: 32 normals of this thread's path -> A buffer, then the tile's 12 MMAs.
+// A Philox block gives six normals (device_math.cuh), so the halves do not fall on block boundaries: half 0
+// draws blocks 0..5 (normals 0..35) and hands normals 32..35 to half 1, which draws blocks 6..10 (36..65, the
+// last two unused).  W[i] is normal 32 * kHalf + i.
+template <int kHalf, bool kFull>
+__device__ __forceinline__ void basket_tc_half(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, BasketTcTile &t,
+                                               float (&carry)[4])
+{
+    constexpr int kNpb = NormalsPerBlock<float>::value;
+    static_assert(kNpb == 6, "the block schedule below is written for six normals per Philox block");
+    constexpr int kPre = kHalf == 0 ? 0 : 4;            // normals inherited from the previous half
+    constexpr int kFirstBlock = kHalf == 0 ? 0 : 6;
+    constexpr int kBlocksHere = kHalf == 0 ? 6 : 5;
+    constexpr int kBlocksFirst16 = (16 - kPre + kNpb - 1) / kNpb;  // blocks needed before columns 0..15 are complete
     const NoShared none;
+    float W[kPre + kNpb * kBlocksHere];
+    if (kPre) {
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        uint32_t hi[16], lo[16];
+        for (int i = 0; i < kPre; i++)
+            W[i] = carry[i];
+    }
+    auto draw = [&](int lb) {
+        uint32_t w[4];
+        philox4x32_10(path_lo, path_hi, (uint32_t)(kFirstBlock + lb), kTagBasket, keys, w);
+        float z[kNpb];
+        normals_from_words(w, z, none);
 #pragma unroll
-        for (int jb = 0; jb < 4; jb++) {
-            uint32_t w[4];
-            philox4x32_10(path_lo, path_hi, (uint32_t)(kHalf * 8 + q * 4 + jb), kTagBasket, keys, w);
-            float z[4];
-            normals_from_words(w, z, none);
+        for (int i = 0; i < kNpb; i++)
+            W[kPre + kNpb * lb + i] = z[i];
+    };
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t h = __float_as_uint(z[i]) & 0xffffe000u;
-                hi[jb * 4 + i] = h;
-                lo[jb * 4 + i] = __float_as_uint(z[i] - __uint_as_float(h));
-            }
-        }
-        if (kHalf == 1 && q == 0)
-            tc::wait_phase(t.bar, 0, t.dead);  // the first half's MMAs have read the A buffer
-        tc::st16(t.lane_d + 64 + q * 16, hi);
-        tc::st16(t.lane_d + 96 + q * 16, lo);
+    for (int lb = 0; lb < kBlocksFirst16; lb++)
+        draw(lb);
+    if (kHalf == 1)
+        tc::wait_phase(t.bar, 0, t.dead);  // the first half's MMAs have read the A buffer
+    basket_tc_store16(W, t.lane_d, 0);
+#pragma unroll
+    for (int lb = kBlocksFirst16; lb < kBlocksHere; lb++)
+        draw(lb);
+    basket_tc_store16(W + 16, t.lane_d, 16);
+    if (kHalf == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            carry[i] = W[32 + i];
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc::fence_before();
@@ -302,8 +335,9 @@ __device__ __forceinline__ void basket_tc_payoff_half(const unsigned long long (
 template <bool kFull>
 __device__ __forceinline__ float basket_tc_path(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, BasketTcTile &t)
 {
-    basket_tc_half<0, kFull>(keys, path_lo, path_hi, t);
-    basket_tc_half<1, kFull>(keys, path_lo, path_hi, t);
+    float carry[4];
+    basket_tc_half<0, kFull>(keys, path_lo, path_hi, t, carry);
+    basket_tc_half<1, kFull>(keys, path_lo, path_hi, t, carry);
     tc::wait_phase(t.bar, 1, t.dead);  // accumulator complete, A buffer free for the next round
     unsigned long long sum2 = pack2(-tc::const_f32<kTcKBase>(), 0.0f);
     {

@@ -78,32 +78,57 @@ __device__ __forceinline__ float mufu_cos(float x)
     return y;
 }
 
-// 23 random bits under the exponent of 1.0f: f in [1, 2) exactly (one LEA.HI)
-__device__ __forceinline__ float stuffed_unit_f32(uint32_t w)
+// fp32: one Philox block (128 bits) serves THREE Box-Muller pairs, i.e. six normals.  Pair i takes 42
+// consecutive bits of the block read as one 128-bit string w0:w1:w2:w3 (w0 most significant): 23 for the
+// radius uniform, then 19 for the angle; the last 2 bits are unused.
+//   radius: the 23 bits become the mantissa of f in [1, 2) exactly; u = 2 - f in (0, 1] (tails to 5.65 sigma)
+//   angle:  the 19 bits become mantissa bits [22:4] of f in [1, 2): 2^19 directions (for anything smooth in the
+//           pair the lattice error is that of a trapezoid rule on a periodic function, i.e. below fp32 rounding)
+// The first version gave every uniform the top 23 bits of its own word (two pairs per block): a third more
+// IMAD.WIDE work -- the instruction that binds the fp32 kernels -- for bits no estimate can see.
+// Field extraction is a funnel shift + one LOP3 ((x & mask) | exponent) per uniform, 11 ALU ops per block.
+__device__ __forceinline__ float stuffed_unit_f32(uint32_t w)  // 23 random bits from the top of a word (one LEA.HI)
 {
     return __uint_as_float(0x3f800000u | (w >> 9));
 }
+__device__ __forceinline__ float stuff_f32(uint32_t window, uint32_t mask)
+{
+    return __uint_as_float((window & mask) | 0x3f800000u);
+}
+__device__ __forceinline__ void uniforms_f32(const uint32_t (&w)[4], float (&f)[6])
+{
+    constexpr uint32_t kRadius = 0x007fffffu, kAngle = 0x007ffff0u;
+    f[0] = stuffed_unit_f32(w[0]);                                    // bits   0.. 22: w0[31:9]
+    f[1] = stuff_f32(__funnelshift_l(w[1], w[0], 14), kAngle);        // bits  23.. 41: w0[8:0] w1[31:22]
+    f[2] = stuff_f32(__funnelshift_l(w[2], w[1], 1), kRadius);        // bits  42.. 64: w1[21:0] w2[31]
+    f[3] = stuff_f32(w[2] >> 8, kAngle);                              // bits  65.. 83: w2[30:12]
+    f[4] = stuff_f32(__funnelshift_l(w[3], w[2], 11), kRadius);       // bits  84..106: w2[11:0] w3[31:21]
+    f[5] = stuff_f32(w[3] << 2, kAngle);                              // bits 107..125: w3[20:2]
+}
 
-// Two words -> one Box-Muller pair.  radius: u = 2 - f in (0, 1], r = sqrt(-2 ln u);
+// One Box-Muller pair from its two stuffed uniforms.  radius: u = 2 - f in (0, 1], r = sqrt(-2 ln u);
 // angle: 2*pi*(f - 1.5) in [-pi, pi) as one FFMA, the range where MUFU.SIN/COS are most accurate.
 // 4 MUFU per pair (LG2, SQRT, SIN, COS).
-__device__ __forceinline__ void box_muller_f32(uint32_t wa, uint32_t wb, float &z0, float &z1)
+__device__ __forceinline__ void box_muller_f32(float fr, float fa, float &z0, float &z1)
 {
-    const float u = 2.0f - stuffed_unit_f32(wa);
+    const float u = 2.0f - fr;
     const float r = mufu_sqrt(mufu_lg2(u) * -1.3862943611198906f);  // -2 ln2 * log2(u)
-    const float a = fmaf(stuffed_unit_f32(wb), 6.283185307179586f, -9.42477796076938f);
+    const float a = fmaf(fa, 6.283185307179586f, -9.42477796076938f);
     z0 = r * mufu_cos(a);
     z1 = r * mufu_sin(a);
 }
 
-__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float (&z)[4], const NoShared &)
+__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float (&z)[6], const NoShared &)
 {
-    box_muller_f32(w[0], w[1], z[0], z[1]);
-    box_muller_f32(w[2], w[3], z[2], z[3]);
+    float f[6];
+    uniforms_f32(w, f);
+    box_muller_f32(f[0], f[1], z[0], z[1]);
+    box_muller_f32(f[2], f[3], z[2], z[3]);
+    box_muller_f32(f[4], f[5], z[4], z[5]);
 }
 
 // ---- fp64 ----
-// One Philox block (128 bits) serves TWO fp64 Box-Muller pairs, i.e. four normals, like fp32.
+// One Philox block (128 bits) serves TWO fp64 Box-Muller pairs, i.e. four normals.
 // Each pair takes 64 bits (wa, wb): the radius uniform gets 44 of them (wa and the top 12 bits of wb,
 // stuffed under the exponent of 1.0: f in [1,2), u = 2 - f in (0,1], tails to 7.8 sigma), the angle
 // the other 20 (a turn fraction k / 2^20: 2^20 directions; for anything smooth in the pair the
@@ -127,8 +152,10 @@ __device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], doubl
     box_muller_f64(w[2], w[3], z[2], z[3], sh.t);
 }
 
-// normals per Philox block, both precisions
-constexpr int kNormalsPerBlock = 4;
+// normals per Philox block
+template <typename Real> struct NormalsPerBlock;
+template <> struct NormalsPerBlock<float> { static constexpr int value = 6; };
+template <> struct NormalsPerBlock<double> { static constexpr int value = 4; };
 
 // max(x, 0): FMNMX for fp32; for fp64 an integer mask (fmax(double) is DSETP + selects + NaN fix-up)
 __device__ __forceinline__ float positive_part(float x) { return fmaxf(x, 0.0f); }

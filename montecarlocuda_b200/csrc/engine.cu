@@ -128,7 +128,8 @@ int fill_plan(int workload, int precision, uint64_t n_paths, double scale_ref, d
     plan->workload = workload;
     plan->precision = precision;
     plan->total_paths = n_paths;
-    plan->unit_paths = workload == MCB200_VANILLA ? 4 : 1;  // one Philox block = four normals
+    // one Philox block = six fp32 or four fp64 normals (device_math.cuh)
+    plan->unit_paths = workload == MCB200_VANILLA ? (precision == MCB200_F32 ? 6 : 4) : 1;
     plan->total_units = (n_paths + plan->unit_paths - 1) / plan->unit_paths;
     plan->rounds = chunk_rounds(plan->total_units);
     plan->chunk_units = (uint64_t)kThreads * plan->rounds;
@@ -922,7 +923,7 @@ int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint3
     uint32_t *d_ctr = nullptr;
     void *d_out = nullptr;
     MCB_CUDA(ctx, cudaMalloc(&d_ctr, n * 16));
-    const size_t out_bytes = n * 4 * (precision == MCB200_F64 ? 8 : 4);  // 4 normals per counter
+    const size_t out_bytes = n * (precision == MCB200_F64 ? 4 * 8 : 6 * 4);  // 4 fp64 / 6 fp32 normals per counter
     cudaError_t e = cudaMalloc(&d_out, out_bytes);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(d_ctr, ctr_host, n * 16, cudaMemcpyHostToDevice, ctx->stream);

@@ -41,7 +41,11 @@
 #define R_SQRT sqrt
 #define R_FABS fabs
 #endif
-#define NORMALS_PER_BLOCK 4 /* one Philox block = two Box-Muller pairs, both precisions */
+#ifdef MCB200_SINGLE
+#define NORMALS_PER_BLOCK 6 /* one Philox block = three single-precision Box-Muller pairs (23-bit radius, 19-bit angle) */
+#else
+#define NORMALS_PER_BLOCK 4 /* ... or two double-precision pairs (44-bit radius, 20-bit angle) */
+#endif
 
 /* ---- printing (MonteCarloHost.c:20-65): same fields, same order ---- */
 void printVect(mc_real *mat, int c)
@@ -194,8 +198,17 @@ static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t 
 static void normals(const uint32_t w[4], mc_real z[NORMALS_PER_BLOCK])
 {
 #ifdef MCB200_SINGLE
-    for (int i = 0; i < 2; i++) {
-        uint32_t b0 = 0x3f800000u | (w[2 * i] >> 9), b1 = 0x3f800000u | (w[2 * i + 1] >> 9);
+    /* the block as one 128-bit string w0:w1:w2:w3; pair i = 23 radius bits, then 19 angle bits (csrc/device_math.cuh) */
+    const uint32_t field[6] = {
+        w[0] >> 9,
+        ((w[0] << 14) | (w[1] >> 18)) & 0x007ffff0u,
+        ((w[1] << 1) | (w[2] >> 31)) & 0x007fffffu,
+        (w[2] >> 8) & 0x007ffff0u,
+        ((w[2] << 11) | (w[3] >> 21)) & 0x007fffffu,
+        (w[3] << 2) & 0x007ffff0u,
+    };
+    for (int i = 0; i < 3; i++) {
+        uint32_t b0 = 0x3f800000u | field[2 * i], b1 = 0x3f800000u | field[2 * i + 1];
         float f0, f1;
         memcpy(&f0, &b0, 4);
         memcpy(&f1, &b1, 4);

@@ -2,7 +2,7 @@
 //
 // Replaces brownianVect + basketPayoff + basketOptMonteCarlo (DP/MonteCarloKernel.cu:74-101,
 // :133-177).  One draw unit = one path; draw block j of the path's sub-stream gives normals
-// 4j .. 4j+3.
+// kNpb * j .. kNpb * j + kNpb - 1 (kNpb = 6 in fp32, 4 in fp64).
 //   x_i    = a_i + sum_j F_ij z_j      F_ij = v_i sqrt(T) L_ij,  a_i = (r - v_i^2/2) T + v_i sqrt(T) d_i
 //   payoff = max(sum_i m_i e^{x_i} - K, 0),  m_i = w_i s_i      (fp32: x in log2 units, 2^x by MUFU.EX2)
 // The mat-vec is a column sweep kept in registers: normal j is produced, applied to the N - j
@@ -159,7 +159,7 @@ struct Basket {
     static constexpr int kUnitPaths = 1;
     static constexpr int kUnroll = 1;
     static constexpr int kMinBlocks = basket_min_blocks(N, (int)sizeof(Real));
-    static constexpr int kNpb = kNormalsPerBlock;
+    static constexpr int kNpb = NormalsPerBlock<RealT>::value;
     struct Params {
         PhiloxKeys keys;
     };
@@ -229,10 +229,13 @@ struct Basket {
         philox4x32_10(path_lo, path_hi, (uint32_t)JB, kTagBasket, P.keys, w);
         Real z[kNpb];
         normals_from_words(w, z, sh);
-        column_if<JB * kNpb + 0>(st, z[0], sh);
-        column_if<JB * kNpb + 1>(st, z[1], sh);
-        column_if<JB * kNpb + 2>(st, z[2], sh);
-        column_if<JB * kNpb + 3>(st, z[3], sh);
+        columns<JB>(st, z, sh, std::make_integer_sequence<int, kNpb>{});
+    }
+    template <int JB, int... kQ>
+    static __device__ __forceinline__ void columns(State &st, const Real (&z)[kNpb], const Shared &sh,
+                                                   std::integer_sequence<int, kQ...>)
+    {
+        (column_if<JB * kNpb + kQ>(st, z[kQ], sh), ...);
     }
     template <int... kJB>
     static __device__ __forceinline__ void sweep(const Params &P, uint32_t path_lo, uint32_t path_hi, State &st,

@@ -57,7 +57,7 @@ struct Cva {
     static constexpr int kUnitPaths = 1;
     static constexpr int kUnroll = 1;
     static constexpr int kMinBlocks = 3;
-    static constexpr int kNpb = kNormalsPerBlock;
+    static constexpr int kNpb = NormalsPerBlock<RealT>::value;
     struct Params {
         PhiloxKeys keys;
         Real y0, mu_dt, sig_dt, k;

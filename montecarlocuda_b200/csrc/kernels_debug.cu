@@ -118,9 +118,9 @@ cudaError_t debug_normals(int precision, unsigned long long n, const uint32_t *d
                           void *d_out, cudaStream_t stream)
 {
     if (precision)
-        debug_normals_kernel<double, 4><<<grid_for(n), kThreads, 0, stream>>>(n, d_ctr, keys, (double *)d_out);
+        debug_normals_kernel<double, NormalsPerBlock<double>::value><<<grid_for(n), kThreads, 0, stream>>>(n, d_ctr, keys, (double *)d_out);
     else
-        debug_normals_kernel<float, 4><<<grid_for(n), kThreads, 0, stream>>>(n, d_ctr, keys, (float *)d_out);
+        debug_normals_kernel<float, NormalsPerBlock<float>::value><<<grid_for(n), kThreads, 0, stream>>>(n, d_ctr, keys, (float *)d_out);
     return cudaGetLastError();
 }
 

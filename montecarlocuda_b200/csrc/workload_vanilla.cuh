@@ -16,7 +16,7 @@ template <> struct VanillaTuning<double> { static constexpr int kMinBlocks = 3, 
 template <typename RealT, int kMinBlocksT = VanillaTuning<RealT>::kMinBlocks, int kUnrollT = VanillaTuning<RealT>::kUnroll>
 struct Vanilla {
     using Real = RealT;
-    static constexpr int kUnitPaths = kNormalsPerBlock;
+    static constexpr int kUnitPaths = NormalsPerBlock<RealT>::value;
     static constexpr int kMinBlocks = kMinBlocksT;
     static constexpr int kUnroll = kUnrollT;
     struct Params {

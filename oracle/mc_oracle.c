@@ -51,10 +51,23 @@ void orc_uniforms_f64(const uint32_t w[4], double f[4])
     }
 }
 
-void orc_uniforms_f32(const uint32_t w[4], float f[4])
+/* fp32: a block serves THREE pairs.  The block is read as one 128-bit string w0:w1:w2:w3 (w0 most
+ * significant); pair i takes 42 consecutive bits: 23 for the radius uniform (the whole mantissa of a float in
+ * [1,2)), then 19 for the angle (mantissa bits [22:4] of a float in [1,2)); the last 2 bits are unused.
+ * f[2i] = radius uniform, f[2i+1] = angle uniform, both stuffed floats in [1,2). */
+void orc_uniforms_f32(const uint32_t w[4], float f[6])
 {
-    for (int i = 0; i < 4; i++) {
-        uint32_t bits = 0x3f800000u | (w[i] >> 9);
+    /* bit k of the string, k = 0 the most significant */
+    for (int i = 0; i < 6; i++) {
+        int off = 42 * (i / 2) + ((i & 1) ? 23 : 0);
+        int len = (i & 1) ? 19 : 23;
+        uint32_t field = 0;
+        for (int b = 0; b < len; b++) {
+            int k = off + b;
+            uint32_t bit = (w[k / 32] >> (31 - k % 32)) & 1u;
+            field = (field << 1) | bit;
+        }
+        uint32_t bits = 0x3f800000u | (field << (23 - len));
         memcpy(&f[i], &bits, 4);
     }
 }
@@ -71,11 +84,11 @@ void orc_normals_f64(const uint32_t w[4], double z[4])
     }
 }
 
-void orc_normals_f32(const uint32_t w[4], float z[4])
+void orc_normals_f32(const uint32_t w[4], float z[6])
 {
-    float f[4];
+    float f[6];
     orc_uniforms_f32(w, f);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         float rad = sqrtf(-2.0f * logf(2.0f - f[2 * i]));
         /* angle in [-pi, pi): 2*pi*(f - 1.5) as one fused multiply-add, like the device */
         float ang = fmaf(f[2 * i + 1], 6.283185307179586f, -9.42477796076938f);
@@ -106,7 +119,7 @@ void orc_normals_f32(const uint32_t w[4], float z[4])
 
 #define REAL float
 #define FN(name) CAT(name, f32)
-#define NPB 4
+#define NPB 6
 #define R_EXP expf
 #define R_LOG logf
 #define R_SQRT sqrtf

@@ -43,10 +43,10 @@ enum { ORC_THREADS = 256, ORC_LANES = 5 };
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* four words -> four normals (two Box-Muller pairs on bit-stuffed uniforms), either precision */
 void orc_normals_f64(const uint32_t w[4], double z[4]);
-void orc_normals_f32(const uint32_t w[4], float z[4]);
+void orc_normals_f32(const uint32_t w[4], float z[6]); /* three pairs per block in single precision */
 /* the exact uniform stage, for bit-exact comparison with the device */
 void orc_uniforms_f64(const uint32_t w[4], double f[4]); /* {radius f in [1,2), angle in turns} x 2 */
-void orc_uniforms_f32(const uint32_t w[4], float f[4]);
+void orc_uniforms_f32(const uint32_t w[4], float f[6]); /* {radius, angle} stuffed floats in [1,2) x 3 */
 
 /* ---- closed forms and helpers ---- */
 double orc_cnd_hastings_f64(double d);

@@ -60,7 +60,7 @@ class Oracle:
             z = (C.c_double * 4)()
             self.lib.orc_normals_f64(w, z)
             return np.array(z, dtype=np.float64)
-        z = (C.c_float * 4)()
+        z = (C.c_float * 6)()  # three Box-Muller pairs per block in single precision
         self.lib.orc_normals_f32(w, z)
         return np.array(z, dtype=np.float32)
 
@@ -70,7 +70,7 @@ class Oracle:
             z = (C.c_double * 4)()
             self.lib.orc_uniforms_f64(w, z)
             return np.array(z, dtype=np.float64)
-        z = (C.c_float * 4)()
+        z = (C.c_float * 6)()
         self.lib.orc_uniforms_f32(w, z)
         return np.array(z, dtype=np.float32)
 

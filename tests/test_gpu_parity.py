@@ -88,7 +88,7 @@ def test_chunk_reduction_bit_exact(engine, oracle, in_float, unit_paths, rounds,
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 def test_vanilla_paths_match_oracle(engine, oracle, prec):
-    n, first, seed = 1 << 14, 4096, 4242
+    n, first, seed = 1 << 14, 4092, 4242  # first path on a draw-unit boundary (6 paths in fp32, 4 in fp64)
     got = engine.vanilla_paths(VAN, first, n, prec, seed).astype(np.float64)
     want = oracle.vanilla_payoffs(VAN.s, VAN.k, VAN.r, VAN.v, VAN.t, seed, first, n, prec).astype(np.float64)
     # fp64: exp(ln S0 + x) vs S0*exp(x): relative 1e-13 of S_T (<= ~300) ; fp32: MUFU chain, 3e-5 relative of S_T

@@ -65,8 +65,8 @@ def test_no_device_fails_loudly(ensure_built):
 def test_plan_geometry(ensure_built, oracle):
     m = ensure_built
     opt = m.OptionData(100.0, 100.0, 0.05, 0.2, 1.0)
-    p = m.plan("vanilla", opt, 1 << 32, "f32")
-    assert (p.unit_paths, p.rounds, p.chunk_units, p.n_chunks) == (4, 64, 16384, 65536)
+    p = m.plan("vanilla", opt, 1 << 32, "f32")  # six fp32 normals per Philox block: 715 827 883 draw units
+    assert (p.unit_paths, p.rounds, p.chunk_units, p.n_chunks) == (6, 32, 8192, 87382)
     assert (p.scale_exp_sum, p.scale_exp_sumsq) == (73, 66) and p.discount == pytest.approx(np.exp(-0.05))
     p = m.plan("vanilla", opt, 1 << 32, "f64")
     assert (p.unit_paths, p.rounds, p.chunk_units, p.n_chunks) == (4, 64, 16384, 65536)
@@ -75,7 +75,9 @@ def test_plan_geometry(ensure_built, oracle):
     assert (p.unit_paths, p.rounds, p.n_chunks, p.discount) == (1, 4, 65536, 1.0)
     for units in (1, 255, 1 << 20, (1 << 25) - 1, 1 << 25, 1 << 27, 1 << 31, 1 << 40):
         assert m.plan("cva", cva, units, "f64").rounds == oracle.chunk_rounds(units)
-    p = m.plan("vanilla", opt, 5, "f32")       # ragged: 5 paths = 2 draw units = 1 chunk
+    p = m.plan("vanilla", opt, 7, "f32")       # ragged: 7 paths = 2 draw units of 6 = 1 chunk
+    assert (p.total_units, p.n_chunks) == (2, 1)
+    p = m.plan("vanilla", opt, 5, "f64")       # ... and 5 paths = 2 draw units of 4 in double precision
     assert (p.total_units, p.n_chunks) == (2, 1)
     with pytest.raises(m.Mcb200Error):
         m.plan("vanilla", opt, 0, "f64")

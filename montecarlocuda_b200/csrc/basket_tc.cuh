@@ -25,7 +25,10 @@
 //     side (256 columns), two CTAs per SM use all 512.  For a triangular factor the second half only
 //     reaches assets 32..63: its MMAs run with N = 32 on the upper half of D.
 //   * pipeline: the MMAs of a half (12 x UMMA 128xNx8) are issued by one thread per tile and complete
-//     asynchronously (tcgen05.commit -> mbarrier) while all threads generate the next 32 normals.
+//     asynchronously (tcgen05.commit -> mbarrier) while all threads generate the next normals: the second half's
+//     while the first half multiplies, and the first three Philox blocks of the NEXT round while the second half
+//     multiplies (the payoff of a round is collected after them).  The hand-off "A buffer written" is a named
+//     barrier on which only the issuing warp waits; the other three warps of the tile arrive and go on.
 //
 // The chunk structure, the per-thread accumulation order and the exact-integer combine are those of
 // mc_accumulate_kernel (device_common.cuh): price and half-width stay bit-identical for any grid
@@ -113,12 +116,23 @@ __device__ __forceinline__ void wait_phase(uint32_t bar, uint32_t parity, bool &
 }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tile_barrier(int tile)
+// "A buffer written" hand-off of one tile (128 worker threads) to the CTA's issuing warp: a named barrier per
+// (tile, K half) on which the workers only ARRIVE (and go on drawing normals) and the issuing warp waits.
+// Two arrivals of a worker on the same barrier are always separated by a wait on the completion of the MMAs that
+// the first one released, so phases cannot mix.
+constexpr int kTcHandoffThreads = 128 + 32;
+template <int kHalf>
+__device__ __forceinline__ void tile_arrive(int tile)
 {
     if (tile == 0)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.arrive %0, %1;" ::"n"(1 + kHalf), "n"(kTcHandoffThreads) : "memory");
     else
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.arrive %0, %1;" ::"n"(3 + kHalf), "n"(kTcHandoffThreads) : "memory");
+}
+template <int kHalf, int kTile>
+__device__ __forceinline__ void tile_await()
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(1 + 2 * kTile + kHalf), "n"(kTcHandoffThreads) : "memory");
 }
 
 // 16 consecutive columns of this thread's tensor-memory lane
@@ -171,7 +185,6 @@ struct BasketTcTile {
     uint32_t bar;      // shared-memory address of the tile's mbarrier
     uint32_t b_hi, b_lo;
     int tile;          // 0 / 1 inside the CTA
-    bool leader;       // issues the tile's MMAs
     bool dead;         // a tensor-core wait timed out
 };
 
@@ -180,7 +193,7 @@ __device__ __forceinline__ BasketTcTile basket_tc_setup(BasketTcShared &sh)
     const int tid = threadIdx.x, warp = tid >> 5;
     // factor: constant table -> hi / lo parts in the operand layout (once per CTA)
     const float *f = reinterpret_cast<const float *>(mcb_basket_table);
-    for (int idx = tid; idx < kTcWidth * kTcWidth; idx += kThreads) {
+    for (int idx = tid; idx < kTcWidth * kTcWidth; idx += blockDim.x) {
         const int n = idx / kTcWidth, k = idx % kTcWidth;
         const float v = f[idx];
         const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
@@ -205,13 +218,12 @@ __device__ __forceinline__ BasketTcTile basket_tc_setup(BasketTcShared &sh)
     __syncthreads();
     tc::fence_after();
     BasketTcTile t;
-    t.tile = tid >> 7;
+    t.tile = (tid >> 7) & 1;  // (the issuing warp, tid >= 256, never uses its view)
     t.tile_d = sh.tmem_base + (uint32_t)t.tile * 128u;
     t.lane_d = t.tile_d + ((uint32_t)((warp & 3) * 32) << 16);
     t.bar = (uint32_t)__cvta_generic_to_shared(&sh.mbar[t.tile]);
     t.b_hi = (uint32_t)__cvta_generic_to_shared(sh.b_hi);
     t.b_lo = (uint32_t)__cvta_generic_to_shared(sh.b_lo);
-    t.leader = (tid & 127) == 0;
     t.dead = false;
     return t;
 }
@@ -238,28 +250,24 @@ __device__ __forceinline__ void basket_tc_store16(const float *z, uint32_t lane_
     tc::st16(lane_d + 96 + col, lo);
 }
 
-// One K half: 32 normals of this thread's path -> A buffer, then the tile's 12 MMAs.
+// Normal generation of one K half (32 normals), in two stages so that the kernel can slide the first stage of the
+// NEXT round in front of the wait for this round's accumulator.
 // A Philox block gives six normals (device_math.cuh), so the halves do not fall on block boundaries: half 0
 // draws blocks 0..5 (normals 0..35) and hands normals 32..35 to half 1, which draws blocks 6..10 (36..65, the
 // last two unused).  W[i] is normal 32 * kHalf + i.
-template <int kHalf, bool kFull>
-__device__ __forceinline__ void basket_tc_half(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, BasketTcTile &t,
-                                               float (&carry)[4])
-{
-    constexpr int kNpb = NormalsPerBlock<float>::value;
+template <int kHalf>
+struct BasketTcHalf {
+    static constexpr int kNpb = NormalsPerBlock<float>::value;
     static_assert(kNpb == 6, "the block schedule below is written for six normals per Philox block");
-    constexpr int kPre = kHalf == 0 ? 0 : 4;            // normals inherited from the previous half
-    constexpr int kFirstBlock = kHalf == 0 ? 0 : 6;
-    constexpr int kBlocksHere = kHalf == 0 ? 6 : 5;
-    constexpr int kBlocksFirst16 = (16 - kPre + kNpb - 1) / kNpb;  // blocks needed before columns 0..15 are complete
-    const NoShared none;
-    float W[kPre + kNpb * kBlocksHere];
-    if (kPre) {
-#pragma unroll
-        for (int i = 0; i < kPre; i++)
-            W[i] = carry[i];
-    }
-    auto draw = [&](int lb) {
+    static constexpr int kPre = kHalf == 0 ? 0 : 4;            // normals inherited from the previous half
+    static constexpr int kFirstBlock = kHalf == 0 ? 0 : 6;
+    static constexpr int kBlocksHere = kHalf == 0 ? 6 : 5;
+    static constexpr int kBlocksFirst16 = (16 - kPre + kNpb - 1) / kNpb;  // blocks needed before columns 0..15 are complete
+    static constexpr int kWindow = kPre + kNpb * kBlocksHere;
+
+    static __device__ __forceinline__ void draw(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, int lb, float *W)
+    {
+        const NoShared none;
         uint32_t w[4];
         philox4x32_10(path_lo, path_hi, (uint32_t)(kFirstBlock + lb), kTagBasket, keys, w);
         float z[kNpb];
@@ -267,43 +275,76 @@ __device__ __forceinline__ void basket_tc_half(const PhiloxKeys &keys, uint32_t 
 #pragma unroll
         for (int i = 0; i < kNpb; i++)
             W[kPre + kNpb * lb + i] = z[i];
-    };
-#pragma unroll
-    for (int lb = 0; lb < kBlocksFirst16; lb++)
-        draw(lb);
-    if (kHalf == 1)
-        tc::wait_phase(t.bar, 0, t.dead);  // the first half's MMAs have read the A buffer
-    basket_tc_store16(W, t.lane_d, 0);
-#pragma unroll
-    for (int lb = kBlocksFirst16; lb < kBlocksHere; lb++)
-        draw(lb);
-    basket_tc_store16(W + 16, t.lane_d, 16);
-    if (kHalf == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            carry[i] = W[32 + i];
     }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    tc::fence_before();
-    tc::tile_barrier(t.tile);
-    if (t.leader) {
+    // stage 1: the blocks that complete columns 0..15 (W[0 .. kPre + 6 * kBlocksFirst16))
+    static __device__ __forceinline__ void first(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, float *W,
+                                                 const float (&carry)[4])
+    {
+        if (kPre) {
+#pragma unroll
+            for (int i = 0; i < kPre; i++)
+                W[i] = carry[i];
+        }
+#pragma unroll
+        for (int lb = 0; lb < kBlocksFirst16; lb++)
+            draw(keys, path_lo, path_hi, lb, W);
+    }
+    // stage 2: store columns 0..15, draw the rest, store columns 16..31, hand the A buffer to the issuing warp,
+    // which enqueues the tile's 12 MMAs.  The A buffer must be free when this is called.
+    template <bool kFull>
+    static __device__ __forceinline__ void rest(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, float *W,
+                                                float (&carry)[4], BasketTcTile &t)
+    {
+        basket_tc_store16(W, t.lane_d, 0);
+#pragma unroll
+        for (int lb = kBlocksFirst16; lb < kBlocksHere; lb++)
+            draw(keys, path_lo, path_hi, lb, W);
+        basket_tc_store16(W + 16, t.lane_d, 16);
+        if (kHalf == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                carry[i] = W[32 + i];
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc::fence_before();
+        tc::tile_arrive<kHalf>(t.tile);
+    }
+};
+
+// The issuing warp's side of a hand-off: wait until the 128 workers of tile kTile have written the A buffer of K
+// half kHalf, then one lane enqueues the tile's 12 MMAs (3xTF32 over four K steps of 8) and their commit.
+template <int kHalf, int kTile, bool kFull>
+__device__ __forceinline__ void basket_tc_issue(uint32_t tmem_base, uint32_t b_hi, uint32_t b_lo, uint32_t bar0)
+{
+    tc::tile_await<kHalf, kTile>();
+    if ((threadIdx.x & 31) == 0) {
         tc::fence_after();
         constexpr bool kUpper = kHalf == 1 && !kFull;     // a triangular factor: normals 32..63 only reach assets 32..63
         constexpr uint32_t n0 = kUpper ? 32 : 0;
         constexpr uint32_t idesc = tc::instr_desc(kUpper ? 32 : 64);
         constexpr uint32_t brow = (n0 / 8) * 128;          // byte offset of row n0 inside a K chunk
+        const uint32_t tile_d = tmem_base + kTile * 128;
 #pragma unroll
         for (int ks = 0; ks < 4; ks++) {                   // one MMA covers K = 8 tf32 = two 16-byte chunks
             const uint32_t koff = brow + (uint32_t)(kHalf * 4 + ks) * 2u * kTcLbo;
-            const uint64_t bh = tc::smem_desc(t.b_hi + koff), bl = tc::smem_desc(t.b_lo + koff);
-            const uint32_t ah = t.tile_d + 64 + ks * 8, al = t.tile_d + 96 + ks * 8;
-            tc::mma_ts(t.tile_d + n0, ah, bh, idesc, (kHalf > 0 || ks > 0) ? 1u : 0u);
-            tc::mma_ts(t.tile_d + n0, al, bh, idesc, 1u);
-            tc::mma_ts(t.tile_d + n0, ah, bl, idesc, 1u);
+            const uint64_t bh = tc::smem_desc(b_hi + koff), bl = tc::smem_desc(b_lo + koff);
+            const uint32_t ah = tile_d + 64 + ks * 8, al = tile_d + 96 + ks * 8;
+            tc::mma_ts(tile_d + n0, ah, bh, idesc, (kHalf > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_ts(tile_d + n0, al, bh, idesc, 1u);
+            tc::mma_ts(tile_d + n0, ah, bl, idesc, 1u);
         }
-        tc::commit(t.bar);
+        tc::commit(bar0 + kTile * 8);
     }
     __syncwarp();
+}
+// one round of both tiles
+template <bool kFull>
+__device__ __forceinline__ void basket_tc_issue_round(uint32_t tmem_base, uint32_t b_hi, uint32_t b_lo, uint32_t bar0)
+{
+    basket_tc_issue<0, 0, kFull>(tmem_base, b_hi, b_lo, bar0);
+    basket_tc_issue<0, 1, kFull>(tmem_base, b_hi, b_lo, bar0);
+    basket_tc_issue<1, 0, kFull>(tmem_base, b_hi, b_lo, bar0);
+    basket_tc_issue<1, 1, kFull>(tmem_base, b_hi, b_lo, bar0);
 }
 
 template <int... kI>
@@ -331,14 +372,24 @@ __device__ __forceinline__ void basket_tc_payoff_half(const unsigned long long (
      ...);
 }
 
-// The payoff of one path (all 256 threads of the CTA call this together, once per chunk round).
+// Everything of a round after the first draws of its half 0 (W0 filled by BasketTcHalf<0>::first): both halves'
+// stores and MMAs.  All 256 threads of the CTA call this together.
 template <bool kFull>
-__device__ __forceinline__ float basket_tc_path(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, BasketTcTile &t)
+__device__ __forceinline__ void basket_tc_enqueue(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, float *W0,
+                                                  BasketTcTile &t)
 {
     float carry[4];
-    basket_tc_half<0, kFull>(keys, path_lo, path_hi, t, carry);
-    basket_tc_half<1, kFull>(keys, path_lo, path_hi, t, carry);
-    tc::wait_phase(t.bar, 1, t.dead);  // accumulator complete, A buffer free for the next round
+    BasketTcHalf<0>::rest<kFull>(keys, path_lo, path_hi, W0, carry, t);
+    float W1[BasketTcHalf<1>::kWindow];
+    BasketTcHalf<1>::first(keys, path_lo, path_hi, W1, carry);
+    tc::wait_phase(t.bar, 0, t.dead);  // the first half's MMAs have read the A buffer
+    BasketTcHalf<1>::rest<kFull>(keys, path_lo, path_hi, W1, carry, t);
+}
+
+// The payoff of the round whose MMAs were enqueued last: waits for the accumulator (which also frees the A buffer).
+__device__ __forceinline__ float basket_tc_collect(BasketTcTile &t)
+{
+    tc::wait_phase(t.bar, 1, t.dead);
     unsigned long long sum2 = pack2(-tc::const_f32<kTcKBase>(), 0.0f);
     {
         unsigned long long d[16];
@@ -350,7 +401,7 @@ __device__ __forceinline__ float basket_tc_path(const PhiloxKeys &keys, uint32_t
         tc::ld32(t.lane_d + 32, d);
         basket_tc_payoff_half(d, sum2, std::make_integer_sequence<int, 16>{}, std::integral_constant<int, 1>{});
     }
-    tc::fence_before();  // the next round's MMAs (issued after the tile barrier) overwrite D
+    tc::fence_before();  // the next round's MMAs (issued after the tile hand-off) overwrite D
     return positive_part(__uint_as_float((uint32_t)sum2) + __uint_as_float((uint32_t)(sum2 >> 32)));
 }
 
@@ -358,10 +409,16 @@ struct BasketTcParams {
     PhiloxKeys keys;
 };
 
-// mc_accumulate_kernel with the tile machinery around it.  Every thread runs every round (the tile
-// barriers need all 128 threads); paths beyond the job's total are computed and not counted.
+// mc_accumulate_kernel with the tile machinery around it.  A CTA is 8 worker warps (the 256 threads of the chunk
+// geometry: every one runs every round, paths beyond the job's total are computed and not counted) plus one
+// issuing warp that does nothing but turn hand-offs into MMAs, so the tensor-core bookkeeping (~12 instructions
+// per UMMA: descriptors, uniform-register moves, election) is off the workers' critical path.  With the issue
+// code on a worker warp the other three warps of its tile waited for it a quarter of the time
+// (profiles/r01i_basket64_f32_tensor_worker_issue.txt).
+constexpr int kTcThreads = kThreads + 32;
+
 template <bool kFull>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kTcThreads, 2)
 basket_tc_accumulate_kernel(const __grid_constant__ BasketTcParams P, const __grid_constant__ Geometry G,
                             unsigned long long *__restrict__ acc)
 {
@@ -370,25 +427,45 @@ basket_tc_accumulate_kernel(const __grid_constant__ BasketTcParams P, const __gr
     scratch_init(sc);
     BasketTcTile t = basket_tc_setup(sh);
     const unsigned long long last = G.first_chunk + G.n_chunks;
-    for (unsigned long long chunk = G.first_chunk + blockIdx.x; chunk < last; chunk += gridDim.x) {
-        const unsigned long long base = chunk * G.chunk_units;
-        const bool whole = base + G.chunk_units <= G.total_paths;
-        const unsigned long long n_valid = whole ? G.chunk_units : (G.total_paths > base ? G.total_paths - base : 0ull);
-        float s = 0, s2 = 0;
+    if (threadIdx.x >= kThreads) {
+        // ---- issuing warp ----
+        const uint32_t tmem_base = sh.tmem_base, bar0 = (uint32_t)__cvta_generic_to_shared(&sh.mbar[0]);
+        for (unsigned long long chunk = G.first_chunk + blockIdx.x; chunk < last; chunk += gridDim.x) {
 #pragma unroll 1
-        for (int k = 0; k < G.rounds; k++) {
-            const unsigned long long unit = base + (unsigned long long)k * kThreads + threadIdx.x;
-            const float v = basket_tc_path<kFull>(P.keys, (uint32_t)base + (uint32_t)(k * kThreads) + threadIdx.x,
-                                                  (uint32_t)(base >> 32), t);
-            if (whole || unit < G.total_paths) {
-                s += v;
-                s2 = fmaf(v, v, s2);
-            }
+            for (int k = 0; k < G.rounds; k++)
+                basket_tc_issue_round<kFull>(tmem_base, t.b_hi, t.b_lo, bar0);
+            __syncthreads();  // the two barriers of chunk_commit
+            __syncthreads();
         }
-        chunk_commit((double)s, (double)s2, n_valid, G, sc);
+    } else {
+        // ---- workers ----
+        for (unsigned long long chunk = G.first_chunk + blockIdx.x; chunk < last; chunk += gridDim.x) {
+            const unsigned long long base = chunk * G.chunk_units;
+            const bool whole = base + G.chunk_units <= G.total_paths;
+            const unsigned long long n_valid = whole ? G.chunk_units : (G.total_paths > base ? G.total_paths - base : 0ull);
+            float s = 0, s2 = 0;
+            const uint32_t lo0 = (uint32_t)base + threadIdx.x, hi = (uint32_t)(base >> 32);
+            const float no_carry[4] = {0.f, 0.f, 0.f, 0.f};
+            float W0[BasketTcHalf<0>::kWindow];
+            BasketTcHalf<0>::first(P.keys, lo0, hi, W0, no_carry);
+#pragma unroll 1
+            for (int k = 0; k < G.rounds; k++) {
+                const unsigned long long unit = base + (unsigned long long)k * kThreads + threadIdx.x;
+                basket_tc_enqueue<kFull>(P.keys, lo0 + (uint32_t)(k * kThreads), hi, W0, t);
+                // software pipeline: the next round's first draws run while this round's last MMAs complete
+                if (k + 1 < G.rounds)
+                    BasketTcHalf<0>::first(P.keys, lo0 + (uint32_t)((k + 1) * kThreads), hi, W0, no_carry);
+                const float v = basket_tc_collect(t);
+                if (whole || unit < G.total_paths) {
+                    s += v;
+                    s2 = fmaf(v, v, s2);
+                }
+            }
+            chunk_commit((double)s, (double)s2, n_valid, G, sc);
+        }
+        if (t.dead && (threadIdx.x & 127) == 0)
+            atomicAdd(&sc.acc[11], 1ull);
     }
-    if (t.dead && (threadIdx.x & 127) == 0)
-        atomicAdd(&sc.acc[11], 1ull);
     __syncthreads();
     scratch_flush(sc, acc);
     basket_tc_teardown(sh);
@@ -396,18 +473,28 @@ basket_tc_accumulate_kernel(const __grid_constant__ BasketTcParams P, const __gr
 
 // Per-path values of units [first_unit, first_unit + n_units) through the same tile machinery.
 template <bool kFull>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kTcThreads, 2)
 basket_tc_paths_kernel(const __grid_constant__ BasketTcParams P, unsigned long long first_unit, unsigned long long n_units,
                        float *__restrict__ out)
 {
     __shared__ BasketTcShared sh;
     BasketTcTile t = basket_tc_setup(sh);
-    for (unsigned long long blk = blockIdx.x; blk * kThreads < n_units; blk += gridDim.x) {
-        const unsigned long long i = blk * kThreads + threadIdx.x;
-        const unsigned long long unit = first_unit + i;
-        const float v = basket_tc_path<kFull>(P.keys, (uint32_t)unit, (uint32_t)(unit >> 32), t);
-        if (i < n_units)
-            out[i] = t.dead ? __int_as_float(0x7fc00000) : v;
+    if (threadIdx.x >= kThreads) {
+        const uint32_t tmem_base = sh.tmem_base, bar0 = (uint32_t)__cvta_generic_to_shared(&sh.mbar[0]);
+        for (unsigned long long blk = blockIdx.x; blk * kThreads < n_units; blk += gridDim.x)
+            basket_tc_issue_round<kFull>(tmem_base, t.b_hi, t.b_lo, bar0);
+    } else {
+        for (unsigned long long blk = blockIdx.x; blk * kThreads < n_units; blk += gridDim.x) {
+            const unsigned long long i = blk * kThreads + threadIdx.x;
+            const unsigned long long unit = first_unit + i;
+            const float no_carry[4] = {0.f, 0.f, 0.f, 0.f};
+            float W0[BasketTcHalf<0>::kWindow];
+            BasketTcHalf<0>::first(P.keys, (uint32_t)unit, (uint32_t)(unit >> 32), W0, no_carry);
+            basket_tc_enqueue<kFull>(P.keys, (uint32_t)unit, (uint32_t)(unit >> 32), W0, t);
+            const float v = basket_tc_collect(t);
+            if (i < n_units)
+                out[i] = t.dead ? __int_as_float(0x7fc00000) : v;
+        }
     }
     basket_tc_teardown(sh);
 }

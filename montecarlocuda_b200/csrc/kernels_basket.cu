@@ -398,10 +398,10 @@ static cudaError_t launch_tc(const BasketJob &job, const Geometry *geom, int gri
         }
     }
     if (geom) {
-        basket_tc_accumulate_kernel<kFull><<<grid, kThreads, 0, stream>>>(p, *geom, d_acc);
+        basket_tc_accumulate_kernel<kFull><<<grid, kTcThreads, 0, stream>>>(p, *geom, d_acc);
     } else {
         const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
-        basket_tc_paths_kernel<kFull><<<(int)(blocks < 296ull ? blocks : 296ull), kThreads, 0, stream>>>(p, first_unit, n_units,
+        basket_tc_paths_kernel<kFull><<<(int)(blocks < 296ull ? blocks : 296ull), kTcThreads, 0, stream>>>(p, first_unit, n_units,
                                                                                                        (float *)d_out);
     }
     return cudaGetLastError();

@@ -2,7 +2,7 @@
 // -> (sum, sum^2), fp32 and fp64 (sm_100a).
 //
 // Replaces callPayoff + vanillaOptMonteCarlo (DP/MonteCarloKernel.cu:67-71, :179-220).
-// One draw unit = one Philox block = 4 (fp32) or 2 (fp64) consecutive paths:
+// One draw unit = one Philox block = 6 (fp32) or 4 (fp64) consecutive paths:
 //   fp32: payoff = max(2^(a + b z) - K, 0),  a = log2(S0) + (r - v^2/2) T log2(e),  b = v sqrt(T) log2(e)
 //   fp64: payoff = max(e^(a + b z) - K, 0),  a = ln(S0) + (r - v^2/2) T,            b = v sqrt(T)
 // so a path costs one FMA and one exponential after its normal.
@@ -19,6 +19,7 @@ static typename Vanilla<Real>::Params narrow(const VanillaJob &job)
     p.a = (Real)job.a;
     p.b = (Real)job.b;
     p.k = (Real)job.k;
+    p.c = (Real)(-1.3862943611198906188 * job.b * job.b);
     return p;
 }
 

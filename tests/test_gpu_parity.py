@@ -283,7 +283,8 @@ def test_dropin_symbols(engine, oracle, precision):
     prec = {"dp": "f64", "sp": "f32"}[precision]
     # n = numBlocks * (sims / numBlocks): 512 * (1000000 // 512) = 999936 paths (reference :508)
     v = lib.dev_vanillaOpt(OptionData(100, 100, 0.05, 0.2, 1.0), 512, 128, 1_000_000)
-    ours = engine.vanilla(VAN, 999_936, prec)
+    # the SP library receives float fields: give our side the same rounded parameters
+    ours = engine.vanilla(m.OptionData(100.0, 100.0, real(0.05).value, real(0.2).value, 1.0), 999_936, prec)
     assert v.Expected == real(ours.Expected).value and v.Confidence == real(ours.Confidence).value
     mo = MultiOptionData()
     a = oracle.chol(np.array([[1, .3, .3], [.3, 1, .3], [.3, .3, 1.0]]), prec)

@@ -5,7 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one pricing job of the workload (BASELINE.json configs), sharded over the N ranks:
-    zero accumulator -> ONE kernel over this rank's chunk range -> ONE int64 all-reduce (N > 1).
+    zero accumulator -> ONE kernel over this rank's chunk range, whose last CTA adds the ranks' integer limbs over
+    peer memory (N > 1; --combine nccl: ONE int64 all-reduce after the kernel instead).
 Headline workload: European call, 2^32 paths, fp64 (BASELINE.json configs[1]); the fp32 run of the
 same config and the other configs are reported under "also" (`--also none` to skip them).
 
@@ -326,6 +327,8 @@ def main():
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--also", default="all", help="'all', 'none' or a comma list of extra workloads reported under 'also'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--combine", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: cross-GPU sum inside the pricing kernel over peer memory (peer) or one NCCL all-reduce after it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
@@ -348,7 +351,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m.load()
-    pricer = ShardedPricer(device=local)
+    pricer = ShardedPricer(device=local, combine=args.combine)
 
     main_run = time_workload(args.workload, w, pricer, dist, torch, rank, world, args.steps, args.warmup, sample_clocks=(rank == 0), gpu_index=local)
     also = {}
@@ -367,12 +370,14 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_run["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": w["prec"], "data": "synthetic",
             "config": {"workload": args.workload, "description": describe(w), "paths": w["paths"], "sharding": f"contiguous chunk ranges over {world} rank(s)",
-                       "collective": "one int64 SUM all-reduce of 96 bytes per step" if world > 1 else "none (1 GPU)",
+                       "collective": "none (1 GPU)" if world == 1 else
+                       ("fused into the pricing kernel: last CTA pushes 96 bytes to every peer mailbox over NVLink and adds the peers' limbs (no separate collective)"
+                        if pricer.combine == "peer" else "one int64 SUM all-reduce (NCCL) of 96 bytes per step" + (f" [{pricer.combine_note}]" if pricer.combine_note else "")),
                        "l2": "not applicable: compute-bound, no resident input (parameters <= 33 KB in the constant bank, output 96 bytes)"},
             "roofline": roofline(w, main_run["value"] / world, main_run["clocks"]),
             "e2e": {"value": main_run["e2e_value"], "unit": unit_name(w), "h2d_bytes_per_step": main_run["params_bytes"] + 208,
                     "d2h_bytes_per_step": 96, "api": "mcb200_vanilla/basket/cva (blocking C-ABI call, host structs in, result out)" if world == 1
-                    else "ShardedPricer.price per rank (launch + all-reduce + read-back + closing)"},
+                    else "ShardedPricer.price per rank (launch + cross-GPU combine + read-back + closing)"},
             "gpu_launches": main_run["launches"], "clocks": main_run["clocks"],
             "price": res.Expected, "std_error": res.std_error, "confidence": res.Confidence,
             "closed_form": 10.450583572185565 if w["kind"] == "vanilla" else None,

@@ -171,6 +171,26 @@ int mcb200_cva_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_c
                       uint64_t seed, uint64_t first_chunk, uint64_t n_chunks,
                       uint64_t *d_acc, void *stream);
 /* host-side closing on a (summed) accumulator block: DP/MonteCarloKernel.cu:412-423, :459-469 */
+/* ---- peer groups: the (sum, sum^2) combine across GPUs fused into the pricing kernel ----
+ * The reference has no multi-GPU path; the collective this replaces is the single 96-byte SUM all-reduce that
+ * follows a sharded launch.  Every rank owns a mailbox in device memory that its peers write over NVLink
+ * (CUDA IPC between processes, peer access inside one).  While a connected group is attached to a context, the
+ * *_launch entry points above end with the combine: the last CTA of each device's kernel pushes the device's
+ * integer limbs into every mailbox, waits for its peers' and adds them, so d_acc holds the JOB's totals on every
+ * rank when the kernel ends (bit-identical everywhere; no separate collective, no extra launch).  Every rank must
+ * issue the same sequence of sharded launches, on streams that can run concurrently with its peers'.
+ *   one process per GPU:   peer_create on every rank -> exchange the 64-byte handles (any transport) -> peer_connect
+ *   one process, many GPUs (or many contexts on one GPU): peer_create for every rank -> peer_connect_local */
+#define MCB200_PEER_HANDLE_BYTES 64
+#define MCB200_PEER_MAX 8
+typedef struct mcb200_peer mcb200_peer;
+int mcb200_peer_create(mcb200_ctx *ctx, int rank, int world, mcb200_peer **out,
+                       unsigned char handle[MCB200_PEER_HANDLE_BYTES]);
+int mcb200_peer_connect(mcb200_peer *peer, const unsigned char *handles /* world x 64 bytes, rank-major */);
+int mcb200_peer_connect_local(mcb200_peer **group, int world);
+int mcb200_peer_attach(mcb200_ctx *ctx, mcb200_peer *peer /* NULL detaches */);
+int mcb200_peer_destroy(mcb200_peer *peer);
+
 int mcb200_finalize(const mcb200_plan_t *plan, const uint64_t acc[MCB200_ACC_WORDS],
                     mcb200_result_t *out);
 

@@ -56,6 +56,7 @@ class PlanT(C.Structure):
                 ("scale_exp_sumsq", C.c_int), ("discount", C.c_double)]
 
 
+PEER_HANDLE_BYTES = 64
 _P = C.POINTER
 _CTX = C.c_void_p
 _SIGNATURES = {
@@ -67,6 +68,11 @@ _SIGNATURES = {
     "mcb200_strerror": (C.c_char_p, [C.c_int]),
     "mcb200_last_error": (C.c_char_p, [_CTX]),
     "mcb200_launch_count": (C.c_uint64, [_CTX]),
+    "mcb200_peer_create": (C.c_int, [_CTX, C.c_int, C.c_int, _P(C.c_void_p), C.c_void_p]),
+    "mcb200_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mcb200_peer_connect_local": (C.c_int, [_P(C.c_void_p), C.c_int]),
+    "mcb200_peer_attach": (C.c_int, [_CTX, C.c_void_p]),
+    "mcb200_peer_destroy": (C.c_int, [C.c_void_p]),
     "mcb200_set_basket_engine": (C.c_int, [C.c_int]),
     "mcb200_get_basket_engine": (C.c_int, []),
     "mcb200_vanilla": (C.c_int, [_CTX, C.c_int, _P(OptionT), C.c_uint64, C.c_uint64, _P(ResultT)]),

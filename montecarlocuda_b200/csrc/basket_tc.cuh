@@ -467,7 +467,7 @@ basket_tc_accumulate_kernel(const __grid_constant__ BasketTcParams P, const __gr
             atomicAdd(&sc.acc[11], 1ull);
     }
     __syncthreads();
-    scratch_flush(sc, acc);
+    finish(sc, acc, G);
     basket_tc_teardown(sh);
 }
 

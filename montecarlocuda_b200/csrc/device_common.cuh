@@ -23,6 +23,23 @@ struct PhiloxKeys {
     uint32_t k1[10];
 };
 
+// Peer-memory combine fused into the pricing kernel (multi-GPU, one process per GPU or one process for all).
+// Every rank owns a small mailbox in its device memory that its peers can write over NVLink (CUDA IPC /
+// peer access); mail[r] is rank r's mailbox as addressed from THIS device.  Slot (seq % kPeerRing, src) holds
+// src's 12 accumulator words and, in word kPeerFlagWord, the sequence number that publishes them.
+constexpr int kPeerMax = 8;
+constexpr int kPeerRing = 4;
+constexpr int kPeerSlotWords = 16;
+constexpr int kPeerFlagWord = 12;
+constexpr size_t kPeerMailboxBytes = (size_t)kPeerRing * kPeerMax * kPeerSlotWords * sizeof(unsigned long long);
+struct PeerLink {
+    int world;                            // <= 1: no combine, the kernel leaves this device's partial in acc
+    int rank;
+    unsigned long long seq;               // this launch's sequence number (>= 1, the same on every rank)
+    unsigned long long *mail[kPeerMax];
+    unsigned int *ticket;                 // this device's "CTAs finished" counter (zero between launches)
+};
+
 // What a launch covers.  All of it derives from the JOB (total paths), never from the GPU count.
 struct Geometry {
     unsigned long long total_paths;
@@ -32,6 +49,7 @@ struct Geometry {
     int rounds;                       // units per thread per chunk
     int scale_exp_sum;                // value * 2^e before the integer split
     int scale_exp_sumsq;
+    PeerLink peer;
 };
 
 // One Philox4x32-10 block.  The 64-bit products compile to IMAD.WIDE.U32, the mixes to LOP3.
@@ -134,6 +152,93 @@ __device__ __forceinline__ void scratch_flush(const BlockScratch &sc, unsigned l
     }
 }
 
+// ---- the collective, fused into the kernel that feeds it ----------------------------------------
+// The (sum, sum^2) combine across GPUs is 96 bytes: as a separate NCCL all-reduce it costs a kernel launch
+// and ~20-30 us of latency after a pricing kernel that, sharded over 8 GPUs, runs for 0.5-10 ms.  Here the
+// LAST CTA of each device's pricing kernel pushes the device's limbs straight into every peer's mailbox
+// (12 x 8-byte stores per peer over NVLink, then a release flag), waits for the peers' flags and adds the
+// integer limbs: when the kernel ends, acc holds the JOB's totals on every rank, bit-identical everywhere
+// (integer addition; the order of arrival cannot matter).  Slot reuse is safe with a ring of 2 or more: a rank
+// cannot finish step s + 1 before every peer has pushed step s + 1, which each peer does after reading step s.
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void peer_combine(unsigned long long *acc, const PeerLink &L)
+{
+    __shared__ bool s_last;
+    __shared__ unsigned int s_late;
+    __threadfence();  // this CTA's atomics on acc are ordered before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(L.ticket, 1u) == gridDim.x - 1;
+        s_late = 0u;
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    // ---- last CTA of this device ----
+    __threadfence();
+    const int tid = threadIdx.x;
+    if (tid == 0)
+        *L.ticket = 0u;  // ready for the next launch on this device (stream order)
+    const size_t slot = (size_t)(L.seq % kPeerRing) * kPeerMax;
+    if (tid < kAccWords * L.world) {
+        const int dst = tid / kAccWords, w = tid % kAccWords;
+        const unsigned long long v = *((volatile unsigned long long *)acc + w);
+        st_relaxed_sys(L.mail[dst] + (slot + L.rank) * kPeerSlotWords + w, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < L.world) {
+        st_release_sys(L.mail[tid] + (slot + L.rank) * kPeerSlotWords + kPeerFlagWord, L.seq);
+        // wait for rank tid's words.  Bounded: a peer that never launches must end as an error flag, not a hang.
+        const unsigned long long *flag = L.mail[L.rank] + (slot + tid) * kPeerSlotWords + kPeerFlagWord;
+        bool ok = false;
+        for (int spin = 0; spin < (1 << 22) && !ok; spin++) {
+            ok = ld_acquire_sys(flag) == L.seq;
+            if (!ok)
+                __nanosleep(64);
+        }
+        if (!ok)
+            atomicAdd(&s_late, 1u);
+    }
+    __syncthreads();
+    if (tid < kAccWords) {
+        unsigned long long total = 0ull;
+        for (int src = 0; src < L.world; src++)
+            total += ld_relaxed_sys(L.mail[L.rank] + (slot + src) * kPeerSlotWords + tid);
+        if (tid == kAccWords - 1 && s_late)
+            total += 1ull;  // error flag: a peer did not answer
+        acc[tid] = total;
+    }
+}
+
+// end of a pricing kernel: CTA totals -> device accumulator (-> job totals on every rank)
+__device__ __forceinline__ void finish(const BlockScratch &sc, unsigned long long *acc, const Geometry &G)
+{
+    scratch_flush(sc, acc);
+    if (G.peer.world > 1)
+        peer_combine(acc, G.peer);
+}
+
 // The pricing kernel skeleton.  W is a workload policy:
 //   W::Real            float or double: the per-path arithmetic type
 //   W::Params          by-value parameter block (constant bank)
@@ -205,7 +310,7 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
         }
         chunk_commit((double)s, (double)s2, n_valid, G, sc);
     }
-    scratch_flush(sc, acc);
+    finish(sc, acc, G);
 }
 
 // Per-path values of units [first_unit, first_unit + n_units): the same W::eval as above.

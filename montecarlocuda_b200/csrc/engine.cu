@@ -35,6 +35,19 @@ struct mcb200_ctx {
     std::string last_error;
     uint64_t launches = 0;
     std::mutex mu;
+    mcb200_peer *peer = nullptr;  // attached peer group: sharded launches combine inside the kernel
+};
+
+// One rank's membership of a peer group (see PeerLink, device_common.cuh).
+struct mcb200_peer {
+    mcb200_ctx *ctx = nullptr;
+    int rank = 0, world = 1;
+    unsigned long long *mailbox = nullptr;          // this rank's mailbox (device memory of ctx->device)
+    unsigned int *ticket = nullptr;
+    unsigned long long *mail[kPeerMax] = {};        // every rank's mailbox as addressed from this device
+    bool opened[kPeerMax] = {};                     // mail[r] came from cudaIpcOpenMemHandle
+    bool connected = false;
+    unsigned long long seq = 0;                     // fused launches so far
 };
 
 namespace {
@@ -346,9 +359,10 @@ int blocks_per_sm(const mcb200_plan_t &plan, const AnyJob &job)
 
 // enqueue one shard on `stream` (device already current)
 int enqueue(mcb200_ctx *ctx, const mcb200_plan_t &plan, const AnyJob &job, uint64_t first_chunk,
-            uint64_t n_chunks, unsigned long long *d_acc, cudaStream_t stream)
+            uint64_t n_chunks, unsigned long long *d_acc, cudaStream_t stream, bool fused = false)
 {
-    if (n_chunks == 0)
+    mcb200_peer *peer = fused ? ctx->peer : nullptr;
+    if (n_chunks == 0 && !peer)
         return MCB200_OK;
     int per_sm = blocks_per_sm(plan, job);
     if (per_sm < 1)
@@ -356,7 +370,17 @@ int enqueue(mcb200_ctx *ctx, const mcb200_plan_t &plan, const AnyJob &job, uint6
     uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
     if (grid > n_chunks)
         grid = n_chunks;
-    const Geometry g = make_geometry(plan, first_chunk, n_chunks);
+    if (grid == 0)
+        grid = 1;  // an empty shard still takes part in the fused combine
+    Geometry g = make_geometry(plan, first_chunk, n_chunks);
+    if (peer) {
+        g.peer.world = peer->world;
+        g.peer.rank = peer->rank;
+        g.peer.seq = ++peer->seq;
+        for (int r = 0; r < peer->world; r++)
+            g.peer.mail[r] = peer->mail[r];
+        g.peer.ticket = peer->ticket;
+    }
     cudaError_t e;
     switch (plan.workload) {
         case MCB200_VANILLA: e = vanilla_launch(plan.precision, job.vanilla, g, (int)grid, d_acc, stream); break;
@@ -547,6 +571,132 @@ int mcb200_set_basket_engine(int engine)
 }
 int mcb200_get_basket_engine(void) { return basket_engine_get(); }
 
+// ---- peer groups: the cross-GPU combine fused into the pricing kernel ----
+int mcb200_peer_create(mcb200_ctx *ctx, int rank, int world, mcb200_peer **out, unsigned char handle[MCB200_PEER_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == MCB200_PEER_HANDLE_BYTES, "IPC handle size");
+    if (!ctx || !out || !handle || world < 1 || world > kPeerMax || rank < 0 || rank >= world)
+        return MCB200_ERR_INVALID;
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    mcb200_peer *p = new (std::nothrow) mcb200_peer;
+    if (!p)
+        return MCB200_ERR_INVALID;
+    p->ctx = ctx;
+    p->rank = rank;
+    p->world = world;
+    cudaError_t e = cudaMalloc(&p->mailbox, kPeerMailboxBytes);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&p->ticket, sizeof(unsigned int));
+    if (e == cudaSuccess)
+        e = cudaMemset(p->mailbox, 0, kPeerMailboxBytes);
+    if (e == cudaSuccess)
+        e = cudaMemset(p->ticket, 0, sizeof(unsigned int));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess)
+        e = cudaIpcGetMemHandle(&h, p->mailbox);
+    if (e == cudaSuccess)
+        e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        if (p->mailbox) cudaFree(p->mailbox);
+        if (p->ticket) cudaFree(p->ticket);
+        delete p;
+        return fail_cuda(ctx, e, "mcb200_peer_create");
+    }
+    std::memcpy(handle, &h, sizeof h);
+    p->mail[rank] = p->mailbox;
+    *out = p;
+    return MCB200_OK;
+}
+
+int mcb200_peer_connect(mcb200_peer *p, const unsigned char *handles)
+{
+    if (!p || !handles || p->connected)
+        return MCB200_ERR_INVALID;
+    mcb200_ctx *ctx = p->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    for (int r = 0; r < p->world; r++) {
+        if (r == p->rank)
+            continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * MCB200_PEER_HANDLE_BYTES, sizeof h);
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail_cuda(ctx, e, "cudaIpcOpenMemHandle (peer mailbox)");
+        p->mail[r] = (unsigned long long *)ptr;
+        p->opened[r] = true;
+    }
+    p->connected = true;
+    return MCB200_OK;
+}
+
+int mcb200_peer_connect_local(mcb200_peer **group, int world)
+{
+    // all ranks live in this process: mailboxes are addressed directly (same device, or peer access between devices)
+    if (!group || world < 1 || world > kPeerMax)
+        return MCB200_ERR_INVALID;
+    for (int r = 0; r < world; r++)
+        if (!group[r] || group[r]->world != world || group[r]->rank != r || group[r]->connected)
+            return MCB200_ERR_INVALID;
+    for (int r = 0; r < world; r++) {
+        mcb200_peer *p = group[r];
+        DeviceGuard guard(p->ctx->device);
+        MCB_CUDA(p->ctx, guard.status());
+        for (int q = 0; q < world; q++) {
+            const int other = group[q]->ctx->device;
+            if (other != p->ctx->device) {
+                int can = 0;
+                MCB_CUDA(p->ctx, cudaDeviceCanAccessPeer(&can, p->ctx->device, other));
+                if (!can)
+                    return fail(p->ctx, MCB200_ERR_UNSUPPORTED, "no peer access between the devices of the group");
+                cudaError_t e = cudaDeviceEnablePeerAccess(other, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail_cuda(p->ctx, e, "cudaDeviceEnablePeerAccess");
+                cudaGetLastError();
+            }
+            p->mail[q] = group[q]->mailbox;
+        }
+        p->connected = true;
+    }
+    return MCB200_OK;
+}
+
+int mcb200_peer_attach(mcb200_ctx *ctx, mcb200_peer *peer)
+{
+    if (!ctx || (peer && (peer->ctx != ctx || !peer->connected)))
+        return MCB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->peer = peer;
+    return MCB200_OK;
+}
+
+int mcb200_peer_destroy(mcb200_peer *p)
+{
+    if (!p)
+        return MCB200_OK;
+    mcb200_ctx *ctx = p->ctx;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        if (ctx->peer == p)
+            ctx->peer = nullptr;
+        DeviceGuard guard(ctx->device);
+        cudaDeviceSynchronize();
+        for (int r = 0; r < p->world; r++)
+            if (p->opened[r])
+                cudaIpcCloseMemHandle(p->mail[r]);
+        if (p->mailbox) cudaFree(p->mailbox);
+        if (p->ticket) cudaFree(p->ticket);
+        cudaGetLastError();
+    }
+    delete p;
+    return MCB200_OK;
+}
+
 const char *mcb200_strerror(int status)
 {
     switch (status) {
@@ -659,7 +809,7 @@ int mcb200_vanilla_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb2
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
     return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
-                   (cudaStream_t)stream);
+                   (cudaStream_t)stream, /*fused=*/true);
 }
 
 int mcb200_basket_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_basket_t *opt, uint64_t seed,
@@ -678,7 +828,7 @@ int mcb200_basket_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb20
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
     return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
-                   (cudaStream_t)stream);
+                   (cudaStream_t)stream, /*fused=*/true);
 }
 
 int mcb200_cva_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_cva_t *cva, uint64_t seed,
@@ -697,7 +847,7 @@ int mcb200_cva_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_c
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
     return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
-                   (cudaStream_t)stream);
+                   (cudaStream_t)stream, /*fused=*/true);
 }
 
 // ---- one-call pricing ----

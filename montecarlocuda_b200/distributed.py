@@ -2,10 +2,15 @@
 
 The job's chunks are split into contiguous ranges, rank g of G owning chunks
 [n_chunks * g / G, n_chunks * (g + 1) / G).  Each rank launches ONE kernel on its GPU, which leaves
-a 96-byte accumulator of exact integer limbs in device memory; ONE int64 SUM all-reduce (NCCL over
-NVLink, enqueued on the same stream as the kernel) combines them.  Integer addition is associative,
-so the combined limbs -- and therefore price and standard error -- are bit-identical for any G and
-any reduction order inside the collective.  The reference has no multi-GPU path.
+a 96-byte accumulator of exact integer limbs in device memory.  The limbs of all ranks are added
+  * "peer" (default on GPUs): inside that same kernel -- its last CTA pushes the limbs into every peer's
+    mailbox over NVLink (CUDA IPC memory), waits for the peers' and adds them (mcb200_peer_*, include/mcb200.h;
+    csrc/device_common.cuh peer_combine): no separate collective, no extra launch;
+  * "nccl": by ONE int64 SUM all-reduce enqueued on the same stream as the kernel (also the gloo path of the
+    CPU tests).
+Integer addition is associative, so the combined limbs -- and therefore price and standard error -- are
+bit-identical for any G, either transport and any order of arrival.  The reference has no multi-GPU path
+(SURVEY.md 2.1).
 """
 from __future__ import annotations
 
@@ -38,12 +43,55 @@ def _launch(engine: Engine, workload: str, p: _lib.PlanT, params, seed: int, fir
                   C.c_void_p(stream)), engine.handle)
 
 
+class PeerGroup:
+    """This rank's membership of a peer-memory combine group, attached to an Engine.  `exchange` turns this
+    rank's 64-byte mailbox handle into the list of all ranks' handles (any transport: here torch.distributed)."""
+
+    def __init__(self, engine: Engine, rank: int, world: int, exchange):
+        self.engine, self.rank, self.world = engine, rank, world
+        lib = engine._lib
+        self._peer = C.c_void_p()
+        handle = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+        _lib.check(lib.mcb200_peer_create(engine.handle, rank, world, C.byref(self._peer), handle), engine.handle)
+        handles = exchange(bytes(handle))
+        if len(handles) != world or any(len(h) != _lib.PEER_HANDLE_BYTES for h in handles):
+            raise ValueError("exchange() must return one 64-byte handle per rank")
+        blob = (C.c_ubyte * (_lib.PEER_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
+        _lib.check(lib.mcb200_peer_connect(self._peer, blob), engine.handle)
+        self.attach()
+
+    def attach(self):
+        _lib.check(self.engine._lib.mcb200_peer_attach(self.engine.handle, self._peer), self.engine.handle)
+
+    def detach(self):
+        _lib.check(self.engine._lib.mcb200_peer_attach(self.engine.handle, None), self.engine.handle)
+
+    def close(self):
+        if self._peer:
+            self.engine._lib.mcb200_peer_destroy(self._peer)
+            self._peer = C.c_void_p()
+
+
+def _exchange_over_process_group(group):
+    import torch.distributed as dist
+
+    def exchange(handle: bytes):
+        out = [None] * dist.get_world_size(group)
+        dist.all_gather_object(out, handle, group=group)
+        return out
+
+    return exchange
+
+
 class ShardedPricer:
-    """One rank's view of a sharded pricing job: persistent engine + device accumulator."""
+    """One rank's view of a sharded pricing job: persistent engine + device accumulator.
+    combine = "peer": the cross-GPU sum runs inside the pricing kernel over peer memory; "nccl": one all-reduce
+    after it; "auto": peer when the group has more than one rank, falling back to nccl (with the reason kept in
+    `combine_note`) only if the peer mailboxes cannot be mapped."""
 
     RING = 32
 
-    def __init__(self, engine: Engine | None = None, device: int | None = None, group=None):
+    def __init__(self, engine: Engine | None = None, device: int | None = None, group=None, combine: str = "auto"):
         import torch
 
         if device is None:
@@ -59,6 +107,29 @@ class ShardedPricer:
         self.host = torch.zeros(_lib.ACC_WORDS, dtype=torch.int64).pin_memory()
         self._job_key = None
         self._job = None
+        self.peers = None
+        self.combine_note = ""
+        rank, world = self._world()
+        if combine not in ("auto", "peer", "nccl"):
+            raise ValueError("combine must be 'auto', 'peer' or 'nccl'")
+        self.combine = "nccl"
+        if world > 1 and combine in ("auto", "peer"):
+            try:
+                with torch.cuda.device(self.device):
+                    self.peers = PeerGroup(self.engine, rank, world, _exchange_over_process_group(self.group))
+                self.combine = "peer"
+            except Exception as exc:  # mapping peer memory can be refused by the platform (IPC disabled, no P2P)
+                if combine == "peer":
+                    raise
+                self.combine_note = f"peer mailboxes unavailable ({exc}); using the NCCL all-reduce"
+            # every rank must take the same route
+            import torch.distributed as dist
+            flag = torch.tensor([1 if self.combine == "peer" else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0 and self.combine == "peer":
+                self.peers.detach()
+                self.combine = "nccl"
+                self.combine_note = "a peer rank could not map the mailboxes; using the NCCL all-reduce"
 
     def _world(self):
         import torch.distributed as dist
@@ -87,7 +158,8 @@ class ShardedPricer:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             _lib.check(fn(self.engine.handle, C.byref(p), C.byref(c_params), seed, first, count,
                           C.c_void_p(self.acc.data_ptr()), C.c_void_p(stream)), self.engine.handle)
-            combine_accumulators(self.acc, self.group)
+            if self.combine != "peer":   # "peer": the kernel itself left the job's totals in acc
+                combine_accumulators(self.acc, self.group)
         return p
 
     def result(self, p: _lib.PlanT) -> OptionValue:
@@ -107,4 +179,4 @@ def price_sharded(workload: str, params, n_paths: int, precision=_lib.F64, seed:
     return pricer.price(workload, params, n_paths, _prec(precision), seed)
 
 
-__all__ = ["ShardedPricer", "combine_accumulators", "price_sharded", "OptionData", "MultiOptionData", "CVA"]
+__all__ = ["PeerGroup", "ShardedPricer", "combine_accumulators", "price_sharded", "OptionData", "MultiOptionData", "CVA"]

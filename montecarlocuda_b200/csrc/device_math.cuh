@@ -152,6 +152,52 @@ __device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], doubl
     box_muller_f64(w[2], w[3], z[2], z[3], sh.t);
 }
 
+// ---- scaled polar form of a block's Box-Muller pairs ---------------------------------------------------
+// A caller that only needs b z (a diffusion step, an exponent), never z itself, takes the pairs as
+// (b r, cos, sin): b z0 = (b r) cos, b z1 = (b r) sin fold into the FMA that consumes them, and the scale b
+// costs nothing because it rides on constants that are there anyway -- fp32: b r = sqrt(lg2(u) * c) with
+// c = -2 ln2 b^2; fp64: b^2 (-2 ln u) = scaled_log_unit(u, c, c_ln2) with c = -2 b^2, c_ln2 = c ln 2.
+// Saves the two multiplies r cos, r sin of every pair.
+template <typename Real> struct PolarScale {
+    Real c, c_ln2;
+};
+template <typename Real> __host__ __device__ inline PolarScale<Real> polar_scale(double b)
+{
+    PolarScale<Real> s;
+    if (sizeof(Real) == 4) {
+        s.c = (Real)(-1.3862943611198906188 * b * b);
+        s.c_ln2 = 0;
+    } else {
+        s.c = (Real)(-2.0 * b * b);
+        s.c_ln2 = (Real)(-2.0 * b * b * 0.69314718055994530942);
+    }
+    return s;
+}
+__device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], float (&br)[3], float (&cs)[3], float (&sn)[3],
+                                                 const NoShared &, const PolarScale<float> &S)
+{
+    float f[6];
+    uniforms_f32(w, f);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        br[i] = mufu_sqrt(mufu_lg2(2.0f - f[2 * i]) * S.c);
+        const float ang = fmaf(f[2 * i + 1], 6.283185307179586f, -9.42477796076938f);
+        cs[i] = mufu_cos(ang);
+        sn[i] = mufu_sin(ang);
+    }
+}
+__device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], double (&br)[2], double (&cs)[2], double (&sn)[2],
+                                                 const SharedTables64 &sh, const PolarScale<double> &S)
+{
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const uint32_t wa = w[2 * i], wb = w[2 * i + 1];
+        const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
+        br[i] = sqrt_pos(fabs(scaled_log_unit(2.0 - f, sh.t, S.c, S.c_ln2)));
+        sincos_turn20(wb & 0x000fffffu, cs[i], sn[i], sh.t);
+    }
+}
+
 // normals per Philox block
 template <typename Real> struct NormalsPerBlock;
 template <> struct NormalsPerBlock<float> { static constexpr int value = 6; };

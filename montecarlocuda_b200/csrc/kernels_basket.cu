@@ -113,7 +113,11 @@ constexpr int basket_min_blocks(int n, int real_bytes)
 {
     // registers: the accumulators + ~44 (fp32) / ~60 (fp64) for generator, normals and loop state
     const int regs = n * real_bytes / 4 + (real_bytes == 8 ? 60 : 44);
-    const int blocks = 65536 / (kThreads * regs);
+    int blocks = 65536 / (kThreads * regs);
+    // fp64 from 8 assets up: at 3 CTAs per SM (80 registers) the sweep spills 56-192 bytes per thread and the
+    // local-memory round trips cost more than the third CTA hides (N=10, 2^28 paths: 9.58 ms -> 8.69 ms at 2 CTAs)
+    if (real_bytes == 8 && n >= 8 && blocks > 2)
+        blocks = 2;
     return blocks < 1 ? 1 : (blocks > 4 ? 4 : blocks);
 }
 

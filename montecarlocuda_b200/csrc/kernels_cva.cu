@@ -60,14 +60,16 @@ struct Cva {
     static constexpr int kNpb = NormalsPerBlock<RealT>::value;
     struct Params {
         PhiloxKeys keys;
-        Real y0, mu_dt, sig_dt, k;
+        Real y0, mu_dt, k;
+        PolarScale<Real> scale;  // of sig_dt = v sqrt(dt), folded under the Box-Muller square root
         int n_dates;  // kept dates
     };
     using Shared = typename SharedFor<Real>::type;
-    static __device__ __forceinline__ void step(const Params &P, const CvaDate<Real> &D, Real z, Real &y,
+    // one exposure date; the diffusion sig_dt z arrives as (sig_dt r) * (cos or sin) and folds into the step's FMA
+    static __device__ __forceinline__ void step(const Params &P, const CvaDate<Real> &D, Real sr, Real trig, Real &y,
                                                 Real &cva, const Shared &sh)
     {
-        y = fma(P.sig_dt, z, y + P.mu_dt);
+        y = fma(sr, trig, y + P.mu_dt);
         const Real s = P.k * exp_real(y, sh);
         const Real d1 = fma(y, D.inv, D.c1);
         const Real d2 = d1 - D.sig;
@@ -91,13 +93,13 @@ struct Cva {
         for (int jb = 0; jb * kNpb < P.n_dates; jb++) {
             uint32_t w[4];
             philox4x32_10(path_lo, path_hi, (uint32_t)jb, kTagCva, P.keys, w);
-            Real z[kNpb];
-            normals_from_words(w, z, sh);
+            Real sr[kNpb / 2], cs[kNpb / 2], sn[kNpb / 2];
+            polar_from_words(w, sr, cs, sn, sh, P.scale);
 #pragma unroll
             for (int q = 0; q < kNpb; q++) {
                 const int j = jb * kNpb + q;
                 if (j < P.n_dates)
-                    step(P, dates[j], z[q], y, cva, sh);
+                    step(P, dates[j], sr[q / 2], (q & 1) ? sn[q / 2] : cs[q / 2], y, cva, sh);
             }
         }
         v[0] = cva;
@@ -111,7 +113,7 @@ static typename Cva<Real>::Params narrow(const CvaJob &job)
     p.keys = job.keys;
     p.y0 = (Real)job.y0;
     p.mu_dt = (Real)job.mu_dt;
-    p.sig_dt = (Real)job.sig_dt;
+    p.scale = polar_scale<Real>(job.sig_dt);
     p.k = (Real)job.k;
     p.n_dates = job.n_dates;
     return p;

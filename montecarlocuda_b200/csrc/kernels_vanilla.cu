@@ -17,9 +17,8 @@ static typename Vanilla<Real>::Params narrow(const VanillaJob &job)
     typename Vanilla<Real>::Params p;
     p.keys = job.keys;
     p.a = (Real)job.a;
-    p.b = (Real)job.b;
     p.k = (Real)job.k;
-    p.c = (Real)(-1.3862943611198906188 * job.b * job.b);
+    p.scale = polar_scale<Real>(job.b);
     return p;
 }
 

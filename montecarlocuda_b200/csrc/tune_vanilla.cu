@@ -55,7 +55,7 @@ void run(const char *name, unsigned long long paths, int sms)
     }
     const double unit = sizeof(Real) == 4 ? 1.4426950408889634 : 1.0;
     p.a = (Real)((std::log(100.0) + (0.05 - 0.02) * 1.0) * unit);
-    p.b = (Real)(0.2 * unit);
+    p.scale = polar_scale<Real>(0.2 * unit);
     p.k = (Real)100.0;
     int bps = 0;
     const float ms = time_variant<W>(p, paths, sms, &bps);

@@ -21,8 +21,8 @@ struct Vanilla {
     static constexpr int kUnroll = kUnrollT;
     struct Params {
         PhiloxKeys keys;
-        Real a, b, k;
-        Real c;  // fp32 only: -2 ln2 * b^2, the diffusion scale folded under the Box-Muller square root
+        Real a, k;
+        PolarScale<Real> scale;  // of b = v sqrt(T) (in the exponent's units), folded under the Box-Muller square root
     };
     using Shared = typename SharedFor<Real>::type;
     static __device__ __forceinline__ float grow(float x, const NoShared &) { return mufu_ex2(x); }
@@ -32,26 +32,15 @@ struct Vanilla {
     {
         uint32_t w[4];
         philox4x32_10(unit_lo, unit_hi, 0u, kVanillaTag, P.keys, w);
-        if constexpr (sizeof(Real) == 4) {
-            // the exponent a + b z needs b r, never z itself: b r = sqrt(lg2(u) * (-2 ln2 b^2)), so the scale rides
-            // on the constant under the square root and a pair costs 9 instructions (5 FP32 + 4 MUFU) before its 2^x
-            float f[6];
-            uniforms_f32(w, f);
+        // the exponent a + b z needs b r, never z itself (device_math.cuh, polar_from_words): a path costs one FMA
+        // and one exponential after its pair's (b r, cos, sin)
+        constexpr int kPairs = kUnitPaths / 2;
+        Real br[kPairs], cs[kPairs], sn[kPairs];
+        polar_from_words(w, br, cs, sn, sh, P.scale);
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const float br = mufu_sqrt(mufu_lg2(2.0f - f[2 * i]) * P.c);
-                const float ang = fmaf(f[2 * i + 1], 6.283185307179586f, -9.42477796076938f);
-                v[2 * i] = positive_part(mufu_ex2(fmaf(br, mufu_cos(ang), P.a)) - P.k);
-                v[2 * i + 1] = positive_part(mufu_ex2(fmaf(br, mufu_sin(ang), P.a)) - P.k);
-            }
-        } else {
-            Real z[kUnitPaths];
-            normals_from_words(w, z, sh);
-#pragma unroll
-            for (int q = 0; q < kUnitPaths; q++) {
-                const Real st = grow(fma(P.b, z[q], P.a), sh);
-                v[q] = positive_part(st - P.k);
-            }
+        for (int i = 0; i < kPairs; i++) {
+            v[2 * i] = positive_part(grow(fma(br[i], cs[i], P.a), sh) - P.k);
+            v[2 * i + 1] = positive_part(grow(fma(br[i], sn[i], P.a), sh) - P.k);
         }
     }
 };

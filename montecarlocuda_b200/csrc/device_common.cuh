@@ -8,6 +8,7 @@
 
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace mcb {
 
@@ -100,32 +101,52 @@ struct BlockScratch {
     unsigned long long acc[kAccWords];
 };
 
-__device__ __forceinline__ void scratch_init(BlockScratch &sc)
+// Barrier of one sub-block: a CTA of the pricing kernel is kSubBlocks independent groups of kThreads threads
+// (each the "block" of the stream definition) that only share read-only tables.  One group: __syncthreads.
+template <int kSubBlocks>
+__device__ __forceinline__ void sub_barrier(int sub)
 {
-    if (threadIdx.x < kAccWords)
-        sc.acc[threadIdx.x] = 0ull;
-    __syncthreads();
+    if constexpr (kSubBlocks == 1)
+        __syncthreads();
+    else if (sub == 0)
+        asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    else if (sub == 1)
+        asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+    else if (sub == 2)
+        asm volatile("bar.sync 3, %0;" ::"n"(kThreads) : "memory");
+    else
+        asm volatile("bar.sync 4, %0;" ::"n"(kThreads) : "memory");
+    static_assert(kSubBlocks <= 4, "one named barrier per sub-block");
+}
+
+template <int kSubBlocks = 1>
+__device__ __forceinline__ void scratch_init(BlockScratch &sc, int sub = 0, int tid = threadIdx.x)
+{
+    if (tid < kAccWords)
+        sc.acc[tid] = 0ull;
+    sub_barrier<kSubBlocks>(sub);
 }
 
 // Fixed-shape reduction of one chunk: xor butterfly inside each warp (offsets 16..1, every lane
 // ends with the same value), then warps 0..7 in order on thread 0, which turns the chunk partial
 // into integer limbs held in shared memory.  The chunk partial depends only on the chunk's
 // per-path values, not on which CTA, SM or GPU ran it.
+template <int kSubBlocks = 1>
 __device__ __forceinline__ void chunk_commit(double s, double s2, unsigned long long n_valid,
-                                             const Geometry &G, BlockScratch &sc)
+                                             const Geometry &G, BlockScratch &sc, int sub = 0, int tid = threadIdx.x)
 {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, off);
         s2 += __shfl_xor_sync(0xffffffffu, s2, off);
     }
-    const int warp = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
+    const int warp = tid >> 5;
+    if ((tid & 31) == 0) {
         sc.s[warp] = s;
         sc.s2[warp] = s2;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    sub_barrier<kSubBlocks>(sub);
+    if (tid == 0) {
         double S = sc.s[0], S2 = sc.s2[0];
 #pragma unroll
         for (int w = 1; w < kWarps; w++) {
@@ -138,17 +159,17 @@ __device__ __forceinline__ void chunk_commit(double s, double s2, unsigned long 
         if (!ok)
             sc.acc[11] += 1ull;
     }
-    __syncthreads();
+    sub_barrier<kSubBlocks>(sub);
 }
 
-// After the CTA's last chunk: 12 integer atomics per CTA.  Integer addition is associative, so
-// the device-wide (and, after the all-reduce, job-wide) totals do not depend on arrival order.
-__device__ __forceinline__ void scratch_flush(const BlockScratch &sc, unsigned long long *acc)
+// After the (sub-)block's last chunk: 12 integer atomics.  Integer addition is associative, so
+// the device-wide (and, after the combine, job-wide) totals do not depend on arrival order.
+__device__ __forceinline__ void scratch_flush(const BlockScratch &sc, unsigned long long *acc, int tid = threadIdx.x)
 {
-    if (threadIdx.x < kAccWords) {
-        const unsigned long long v = sc.acc[threadIdx.x];
+    if (tid < kAccWords) {
+        const unsigned long long v = sc.acc[tid];
         if (v != 0ull)
-            atomicAdd(acc + threadIdx.x, v);
+            atomicAdd(acc + tid, v);
     }
 }
 
@@ -232,9 +253,9 @@ __device__ __forceinline__ void peer_combine(unsigned long long *acc, const Peer
 }
 
 // end of a pricing kernel: CTA totals -> device accumulator (-> job totals on every rank)
-__device__ __forceinline__ void finish(const BlockScratch &sc, unsigned long long *acc, const Geometry &G)
+__device__ __forceinline__ void finish(const BlockScratch &sc, unsigned long long *acc, const Geometry &G, int tid = threadIdx.x)
 {
-    scratch_flush(sc, acc);
+    scratch_flush(sc, acc, tid);
     if (G.peer.world > 1)
         peer_combine(acc, G.peer);
 }
@@ -252,17 +273,27 @@ __device__ __forceinline__ void finish(const BlockScratch &sc, unsigned long lon
 // base + k * 256 + t for k < rounds, in that order, and accumulates value and value^2 in W::Real
 // (short runs: at most rounds * kUnitPaths <= 256 terms) before the fp64 block reduction.
 template <class W>
-__global__ void __launch_bounds__(kThreads, W::kMinBlocks)
+__global__ void __launch_bounds__(kThreads * W::kSubBlocks, W::kMinBlocks)
 mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_constant__ Geometry G,
                      unsigned long long *__restrict__ acc)
 {
     using Real = typename W::Real;
-    __shared__ BlockScratch sc;
-    __shared__ typename W::Shared sh;
+    constexpr int kSub = W::kSubBlocks;
+    // W::Shared in dynamic shared memory (the replicated fp64 tables are 96 KB); nothing for fp32
+    extern __shared__ __align__(16) unsigned char mcb_dynamic_smem[];
+    typename W::Shared &sh = *reinterpret_cast<typename W::Shared *>(mcb_dynamic_smem);
+    __shared__ BlockScratch scs[kSub];
+    // sub-block = the "block" of the stream definition: kThreads threads, its own scratch, its own chunks
+    const int sub = kSub == 1 ? 0 : (int)(threadIdx.x / kThreads);
+    const int tid = kSub == 1 ? (int)threadIdx.x : (int)(threadIdx.x % kThreads);
+    BlockScratch &sc = scs[sub];
     sh.load();
-    scratch_init(sc);
+    if (tid < kAccWords)
+        sc.acc[tid] = 0ull;
+    __syncthreads();
     const unsigned long long last = G.first_chunk + G.n_chunks;
-    for (unsigned long long chunk = G.first_chunk + blockIdx.x; chunk < last; chunk += gridDim.x) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * kSub;
+    for (unsigned long long chunk = G.first_chunk + (unsigned long long)blockIdx.x * kSub + sub; chunk < last; chunk += stride) {
         const unsigned long long base = chunk * G.chunk_units;
         const unsigned long long path_end = (base + G.chunk_units) * (unsigned long long)W::kUnitPaths;
         Real s = 0, s2 = 0;
@@ -279,11 +310,11 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
             // (large) estimator body is instantiated once
 #pragma unroll W::kUnroll
             for (int k = 0; k < G.rounds; k++) {
-                const unsigned long long unit = base + (unsigned long long)k * kThreads + threadIdx.x;
+                const unsigned long long unit = base + (unsigned long long)k * kThreads + tid;
                 if (W::kUnitPaths == 1 && !whole && unit >= G.total_paths)
                     break;
                 Real v[W::kUnitPaths];
-                W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + threadIdx.x, (uint32_t)(base >> 32), v, sh);
+                W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh);
 #pragma unroll
                 for (int q = 0; q < W::kUnitPaths; q++) {
                     s += v[q];
@@ -294,11 +325,11 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
             // the job's last chunk with several paths per unit: mask paths beyond the total
 #pragma unroll 1
             for (int k = 0; k < G.rounds; k++) {
-                const unsigned long long unit = base + (unsigned long long)k * kThreads + threadIdx.x;
+                const unsigned long long unit = base + (unsigned long long)k * kThreads + tid;
                 if (unit * (unsigned long long)W::kUnitPaths >= G.total_paths)
                     break;
                 Real v[W::kUnitPaths];
-                W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + threadIdx.x, (uint32_t)(base >> 32), v, sh);
+                W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh);
 #pragma unroll
                 for (int q = 0; q < W::kUnitPaths; q++) {
                     if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths) {
@@ -308,9 +339,52 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
                 }
             }
         }
-        chunk_commit((double)s, (double)s2, n_valid, G, sc);
+        chunk_commit<kSub>((double)s, (double)s2, n_valid, G, sc, sub, tid);
     }
-    finish(sc, acc, G);
+    if constexpr (kSub > 1)
+        __syncthreads();  // every sub-block has committed its last chunk before the CTA-wide tail
+    finish(sc, acc, G, tid);
+}
+
+// Host side of a launch: dynamic shared memory = W::Shared (opt-in above 48 KB, set once per instantiation).
+template <class W> constexpr size_t accumulate_smem_bytes() { return std::is_empty<typename W::Shared>::value ? 0 : sizeof(typename W::Shared); }
+template <class W> inline cudaError_t accumulate_prepare()
+{
+    // a function attribute is per device: set it once on each device this process prices on
+    static bool done[64] = {};
+    if (accumulate_smem_bytes<W>() <= 48 * 1024)
+        return cudaSuccess;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess || device < 0 || device >= 64)
+        return e != cudaSuccess ? e : cudaErrorInvalidDevice;
+    if (!done[device]) {
+        e = cudaFuncSetAttribute(mc_accumulate_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)accumulate_smem_bytes<W>());
+        if (e != cudaSuccess)
+            return e;
+        done[device] = true;
+    }
+    return cudaSuccess;
+}
+template <class W>
+inline cudaError_t accumulate_launch(int grid, const typename W::Params &p, const Geometry &g, unsigned long long *d_acc,
+                                     cudaStream_t stream)
+{
+    cudaError_t e = accumulate_prepare<W>();
+    if (e != cudaSuccess)
+        return e;
+    mc_accumulate_kernel<W><<<grid, kThreads * W::kSubBlocks, accumulate_smem_bytes<W>(), stream>>>(p, g, d_acc);
+    return cudaGetLastError();
+}
+template <class W> inline int accumulate_blocks_per_sm()
+{
+    int n = 0;
+    if (accumulate_prepare<W>() != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mc_accumulate_kernel<W>, kThreads * W::kSubBlocks,
+                                                      accumulate_smem_bytes<W>()) != cudaSuccess)
+        return 0;
+    return n;
 }
 
 // Per-path values of units [first_unit, first_unit + n_units): the same W::eval as above.

@@ -36,9 +36,31 @@ struct SharedTables64 {
         }
     }
 };
+// the same tables in the bank-conflict-free layout (device_math64.cuh), for the pricing kernels
+struct SharedTables64Rep {
+    Tables64Rep t;
+    __device__ __forceinline__ void load()
+    {
+        for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+            t.log_rep[i >> 3][i & 7][0] = kLogTable[i >> 3][0];
+            t.log_rep[i >> 3][i & 7][1] = kLogTable[i >> 3][1];
+        }
+        for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x)
+            t.exp_rep[i >> 4][i & 15] = kExpTable[i >> 4];
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            t.turn_hi[i][0] = kTurnHiTable[i][0];
+            t.turn_hi[i][1] = kTurnHiTable[i][1];
+            t.turn_lo[i][0] = kTurnLoTable[i][0];
+            t.turn_lo[i][1] = kTurnLoTable[i][1];
+        }
+    }
+};
 template <typename Real> struct SharedFor;
 template <> struct SharedFor<float> { using type = NoShared; };
 template <> struct SharedFor<double> { using type = SharedTables64; };
+// what mc_accumulate_kernel instantiates a workload with
+template <typename Real> struct SharedAccumFor { using type = typename SharedFor<Real>::type; };
+template <> struct SharedAccumFor<double> { using type = SharedTables64Rep; };
 
 // ---- fp32: every transcendental is ONE MUFU op (no denormal fix-up, no range-reduction code) ----
 __device__ __forceinline__ float mufu_lg2(float x)
@@ -136,7 +158,8 @@ __device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float
 // The first version spent a whole block per pair (52-bit radius and angle): twice the IMAD.WIDE
 // work for bits no estimate can see.  All arithmetic after the bits is fp64: 12 (log) + 7 (sqrt) +
 // 4 (cos/sin from the two-level table) + 2 = 25 fp64 instructions per pair (libdevice: 68+).
-__device__ __forceinline__ void box_muller_f64(uint32_t wa, uint32_t wb, double &z0, double &z1, const Tables64 &T)
+template <class Tab>
+__device__ __forceinline__ void box_muller_f64(uint32_t wa, uint32_t wb, double &z0, double &z1, const Tab &T)
 {
     const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
     const double r = sqrt_pos(fabs(neg2log_unit(2.0 - f, T)));
@@ -146,7 +169,8 @@ __device__ __forceinline__ void box_muller_f64(uint32_t wa, uint32_t wb, double 
     z1 = r * sn;
 }
 
-__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], double (&z)[4], const SharedTables64 &sh)
+template <class Sh>
+__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], double (&z)[4], const Sh &sh)
 {
     box_muller_f64(w[0], w[1], z[0], z[1], sh.t);
     box_muller_f64(w[2], w[3], z[2], z[3], sh.t);
@@ -186,8 +210,9 @@ __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], float (
         sn[i] = mufu_sin(ang);
     }
 }
+template <class Sh>
 __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], double (&br)[2], double (&cs)[2], double (&sn)[2],
-                                                 const SharedTables64 &sh, const PolarScale<double> &S)
+                                                 const Sh &sh, const PolarScale<double> &S)
 {
 #pragma unroll
     for (int i = 0; i < 2; i++) {
@@ -209,7 +234,7 @@ __device__ __forceinline__ double positive_part(double x) { return relu64(x); }
 
 // precision-generic wrappers used by the workload policies
 __device__ __forceinline__ float exp_real(float x, const NoShared &) { return mufu_ex2(x * 1.4426950408889634f); }
-__device__ __forceinline__ double exp_real(double x, const SharedTables64 &sh) { return exp_tab(x, sh.t); }
+template <class Sh> __device__ __forceinline__ double exp_real(double x, const Sh &sh) { return exp_tab(x, sh.t); }
 __device__ __forceinline__ float rcp_real(float x) { return mufu_rcp(x); }
 __device__ __forceinline__ double rcp_real(double x) { return rcp_newton(x); }
 

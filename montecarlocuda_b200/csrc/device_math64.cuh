@@ -77,24 +77,56 @@ MCB_FN double rcp_seed(double x)
 #endif
 
 // The tables live in shared memory inside the kernels (random per-thread indices: a constant-bank
-// read would serialise); this is the view the functions take.
+// read would serialise); this is the view the functions take.  Plain layout: host build, instrumentation
+// and per-path kernels.
 struct Tables64 {
     double log_tab[256][2];       // { c_i, -ln c_i }
     double exp_tab[256];          // 2^(j/256)
     double turn_hi[1024][2];      // { cos, sin } of 2 pi i / 1024
     double turn_lo[1024][2];      // { cos, sin } of 2 pi j / 2^20
+    MCB_FN void log_entry(int i, double &c, double &l) const { c = log_tab[i][0]; l = log_tab[i][1]; }
+    MCB_FN double exp_entry(int j) const { return exp_tab[j]; }
+    MCB_FN void turn_hi_entry(uint32_t i, double &c, double &s) const { c = turn_hi[i][0]; s = turn_hi[i][1]; }
+    MCB_FN void turn_lo_entry(uint32_t j, double &c, double &s) const { c = turn_lo[j][0]; s = turn_lo[j][1]; }
 };
+
+#ifndef MCB_HOST_MATH
+// Bank-conflict-free layout for the pricing kernels.  The indices are random per thread, so in the plain layout
+// the 8 threads of a quarter-warp (16-byte loads) or the 16 of a half-warp (8-byte loads) collide in the 32
+// shared-memory banks: ~2.7 wavefronts where 1 would do.  ncu on the plain layout (profiles/r01j_vanilla_f64_2p32.txt):
+// 62 % of all shared-memory wavefronts were bank conflicts and the shared-memory pipe was 97 % busy -- the
+// European-call fp64 kernel was bound by it, not by the fp64 pipe.  Here the two small tables are replicated once
+// per bank group: thread t reads replica t % 8 (16-byte entries: 128 bytes per index, one bank group per replica)
+// or t % 16 (8-byte entries), so threads that are served together can never share a bank.  Same values, same
+// arithmetic, bit-identical results; 64 KB instead of 6 KB, shared by all warps of a (large) CTA.
+struct Tables64Rep {
+    double log_rep[256][8][2];    // [index][replica]{ c_i, -ln c_i }
+    double exp_rep[256][16];      // [index][replica] 2^(j/256)
+    double turn_hi[1024][2];
+    double turn_lo[1024][2];
+    MCB_FN void log_entry(int i, double &c, double &l) const
+    {
+        const double2 v = *reinterpret_cast<const double2 *>(&log_rep[i][threadIdx.x & 7][0]);
+        c = v.x;
+        l = v.y;
+    }
+    MCB_FN double exp_entry(int j) const { return exp_rep[j][threadIdx.x & 15]; }
+    MCB_FN void turn_hi_entry(uint32_t i, double &c, double &s) const { c = turn_hi[i][0]; s = turn_hi[i][1]; }
+    MCB_FN void turn_lo_entry(uint32_t j, double &c, double &s) const { c = turn_lo[j][0]; s = turn_lo[j][1]; }
+};
+#endif
 
 // ---- cos and sin of 2 pi k / 2^20 for a 20-bit integer k (the Box-Muller angle of the kernels) ---
 // Two-level table: k = 1024 i + j, angle = coarse_i + fine_j, and the addition theorems give the
 // result from four correctly rounded table values with 2 multiplies + 2 FMAs (abs error < 2 ulp of
 // 1).  Two 16-byte shared-memory loads replace 19 fp64 and ~20 integer instructions of the
 // polynomial version below (sincos_turn), which stays as the reference implementation in the tests.
-MCB_FN void sincos_turn20(uint32_t k, double &cs, double &sn, const Tables64 &T)
+template <class Tab> MCB_FN void sincos_turn20(uint32_t k, double &cs, double &sn, const Tab &T)
 {
     const uint32_t i = (k >> 10) & 1023u, j = k & 1023u;
-    const double ch = T.turn_hi[i][0], sh = T.turn_hi[i][1];
-    const double cl = T.turn_lo[j][0], sl = T.turn_lo[j][1];
+    double ch, sh, cl, sl;
+    T.turn_hi_entry(i, ch, sh);
+    T.turn_lo_entry(j, cl, sl);
     cs = fma_(-sh, sl, ch * cl);
     sn = fma_(ch, sl, sh * cl);
 }
@@ -103,15 +135,15 @@ MCB_FN void sincos_turn20(uint32_t k, double &cs, double &sn, const Tables64 &T)
 // u = 2^e m, m in [1,2); i = top 8 mantissa bits; r = m c_i - 1 in [0, 2^-8);
 // ln u = e ln2 + (-ln c_i) + log1p(r), log1p by its degree-6 Taylor polynomial (|error| < 2^-59).
 // The result can come out as -1e-17 instead of +0 when u is one ulp below 1; callers take |.|.
-MCB_FN double neg2log_unit(double u, const Tables64 &T)
+template <class Tab> MCB_FN double neg2log_unit(double u, const Tab &T)
 {
     const int hi = hi_word(u);
     const int idx = (hi >> 12) & 0xff;
     const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(u));
     // exponent as a double without a conversion instruction: 2^52 + biased exponent, minus (2^52 + 1023)
     const double e = make_double(0x43300000, (int)((unsigned)hi >> 20)) - 4503599627371519.0;
-    const double c = T.log_tab[idx][0];
-    const double l = T.log_tab[idx][1];
+    double c, l;
+    T.log_entry(idx, c, l);
     const double r = fma_(m, c, -1.0);
     double q = fma_(r, -1.0 / 6.0, 0.2);
     q = fma_(r, q, -0.25);
@@ -127,14 +159,14 @@ MCB_FN double neg2log_unit(double u, const Tables64 &T)
 // k * ln(u) for a caller-chosen k (k_ln2 = k ln 2): the scale rides on the three constants of the final FMAs, so
 // e.g. b^2 (-2 ln u) -- the squared radius of a Box-Muller pair already multiplied by a diffusion scale b --
 // costs the same 12 instructions as -2 ln u.  neg2log_unit(u) == scaled_log_unit(u, -2, -2 ln 2).
-MCB_FN double scaled_log_unit(double u, const Tables64 &T, double k, double k_ln2)
+template <class Tab> MCB_FN double scaled_log_unit(double u, const Tab &T, double k, double k_ln2)
 {
     const int hi = hi_word(u);
     const int idx = (hi >> 12) & 0xff;
     const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(u));
     const double e = make_double(0x43300000, (int)((unsigned)hi >> 20)) - 4503599627371519.0;
-    const double c = T.log_tab[idx][0];
-    const double l = T.log_tab[idx][1];
+    double c, l;
+    T.log_entry(idx, c, l);
     const double r = fma_(m, c, -1.0);
     double q = fma_(r, -1.0 / 6.0, 0.2);
     q = fma_(r, q, -0.25);
@@ -213,7 +245,7 @@ MCB_FN void sincos_turn(uint32_t k_hi, uint32_t k_lo, double &cs, double &sn)
 // e^x = 2^(n>>8) * T[n & 255] * (1 + r + r^2/2 + r^3/6 + r^4/24).  The power of two is added to the
 // exponent field as an integer, so the argument must satisfy |x| <= 700: the host validates every
 // job's reachable exponent range (engine.cu: make_*_job) and the CVA kernel floors -d^2/2 at -700.
-MCB_FN double exp_tab(double x, const Tables64 &T)
+template <class Tab> MCB_FN double exp_tab(double x, const Tab &T)
 {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52
     const double t = fma_(x, 0x1.71547652b82fep+8, magic);
@@ -221,7 +253,7 @@ MCB_FN double exp_tab(double x, const Tables64 &T)
     const double nd = t - magic;
     double r = fma_(nd, -0x1.62e42fee00000p-9, x);
     r = fma_(nd, -0x1.a39ef35793c76p-41, r);
-    const double tj = T.exp_tab[n & 255];
+    const double tj = T.exp_entry(n & 255);
     double p = fma_(r, 1.0 / 24.0, 1.0 / 6.0);
     p = fma_(r, p, 0.5);
     p = fma_(r * r, p, r);          // e^r - 1

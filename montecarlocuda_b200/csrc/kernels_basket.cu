@@ -155,22 +155,30 @@ __device__ __forceinline__ void packed_fma_pair(unsigned long long &x2, unsigned
                  : "l"(zz), "r"(base), "n"(kByteOffset));
 }
 
-template <typename RealT, int N, bool kFull>
+template <typename RealT, int N, bool kFull, bool kAccumLayout = false>
 struct Basket {
     using Real = RealT;
     using Table = BasketTable<Real, N, kFull>;
     static_assert(sizeof(Table) <= kBasketTableBytes, "basket table exceeds its constant buffer");
     static constexpr int kUnitPaths = 1;
     static constexpr int kUnroll = 1;
-    static constexpr int kMinBlocks = basket_min_blocks(N, (int)sizeof(Real));
+    // fp64: the CTAs of 256 threads an SM holds become ONE CTA of that many sub-blocks around one (replicated) table set
+    static constexpr int kSubBlocks = (kAccumLayout && sizeof(RealT) == 8) ? basket_min_blocks(N, 8) : 1;
+    static constexpr int kMinBlocks = kSubBlocks > 1 ? 1 : basket_min_blocks(N, (int)sizeof(Real));
     static constexpr int kNpb = NormalsPerBlock<RealT>::value;
     struct Params {
         PhiloxKeys keys;
     };
     static constexpr bool kSharedFactor = Table::kSharedFactor;
-    using Shared = std::conditional_t<kSharedFactor, SharedFactor<(kSharedFactor ? Table::kFactor : 1)>, typename SharedFor<Real>::type>;
-    static __device__ __forceinline__ float grow(float x, const NoShared &) { return mufu_ex2(x); }
-    static __device__ __forceinline__ double grow(double x, const SharedTables64 &sh) { return exp_tab(x, sh.t); }
+    using Shared = std::conditional_t<kSharedFactor, SharedFactor<(kSharedFactor ? Table::kFactor : 1)>,
+                                      std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>>;
+    template <class Sh> static __device__ __forceinline__ Real grow(Real x, const Sh &sh)
+    {
+        if constexpr (sizeof(Real) == 4)
+            return mufu_ex2(x);
+        else
+            return exp_tab(x, sh.t);
+    }
     static constexpr int kBlocks = (N + kNpb - 1) / kNpb;
     static constexpr int kFactorBase = 0;
     static constexpr int kABase = Table::kFactor * (int)sizeof(Real);
@@ -313,10 +321,13 @@ static cudaError_t launch_t(const BasketJob &job, const Geometry *geom, int grid
                             cudaStream_t stream)
 {
     using W = Basket<Real, N, kFull>;
+    using WA = Basket<Real, N, kFull, true>;
     std::vector<unsigned char> staging(sizeof(typename W::Table));
     fill_table(job, *reinterpret_cast<typename W::Table *>(staging.data()));
     typename W::Params p;
     p.keys = job.keys;
+    typename WA::Params pa;
+    pa.keys = job.keys;
     TableUse use(g_basket_lock, stream, staging.data(), staging.size());
     if (use.status() != cudaSuccess)
         return use.status();
@@ -328,24 +339,18 @@ static cudaError_t launch_t(const BasketJob &job, const Geometry *geom, int grid
             return e;
         }
     }
-    if (geom) {
-        mc_accumulate_kernel<W><<<grid, kThreads, 0, stream>>>(p, *geom, d_acc);
-    } else {
-        const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
-        mc_paths_kernel<W><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(
-            p, first_unit, n_units, (Real *)d_out);
-    }
+    if (geom)
+        return accumulate_launch<WA>(grid, pa, *geom, d_acc, stream);
+    const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
+    mc_paths_kernel<W><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(p, first_unit, n_units,
+                                                                                               (Real *)d_out);
     return cudaGetLastError();
 }
 
 template <typename Real, int N, bool kFull>
 static int occupancy_t()
 {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mc_accumulate_kernel<Basket<Real, N, kFull>>, kThreads,
-                                                      0) != cudaSuccess)
-        return 0;
-    return n;
+    return accumulate_blocks_per_sm<Basket<Real, N, kFull, true>>();
 }
 
 // ---- tensor-core engine (basket_tc.cuh): fp32, 32 < n <= 64 ----

@@ -12,6 +12,7 @@
 // so a path-step costs one normal, two exponentials and two reciprocals; the reference spends six
 // exponentials, a log, three square roots and four divisions on it.  Dates the reference drops
 // (remaining time rounded below zero) are simply absent from the table.
+#include <type_traits>
 #include <vector>
 
 #include "device_math.cuh"
@@ -51,12 +52,13 @@ __device__ __forceinline__ double floor_at_minus_700(double a)
 }
 __device__ __forceinline__ float floor_at_minus_700(float a) { return a; }  // MUFU.EX2(-inf) = 0
 
-template <typename RealT>
+template <typename RealT, bool kAccumLayout = false>
 struct Cva {
     using Real = RealT;
     static constexpr int kUnitPaths = 1;
     static constexpr int kUnroll = 1;
-    static constexpr int kMinBlocks = 3;
+    static constexpr int kSubBlocks = (kAccumLayout && sizeof(RealT) == 8) ? 3 : 1;  // fp64: one table set per SM
+    static constexpr int kMinBlocks = kSubBlocks > 1 ? 1 : 3;
     static constexpr int kNpb = NormalsPerBlock<RealT>::value;
     struct Params {
         PhiloxKeys keys;
@@ -64,7 +66,7 @@ struct Cva {
         PolarScale<Real> scale;  // of sig_dt = v sqrt(dt), folded under the Box-Muller square root
         int n_dates;  // kept dates
     };
-    using Shared = typename SharedFor<Real>::type;
+    using Shared = std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>;
     // one exposure date; the diffusion sig_dt z arrives as (sig_dt r) * (cos or sin) and folds into the step's FMA
     static __device__ __forceinline__ void step(const Params &P, const CvaDate<Real> &D, Real sr, Real trig, Real &y,
                                                 Real &cva, const Shared &sh)
@@ -106,10 +108,11 @@ struct Cva {
     }
 };
 
-template <typename Real>
-static typename Cva<Real>::Params narrow(const CvaJob &job)
+template <class W>
+static typename W::Params narrow(const CvaJob &job)
 {
-    typename Cva<Real>::Params p;
+    using Real = typename W::Real;
+    typename W::Params p;
     p.keys = job.keys;
     p.y0 = (Real)job.y0;
     p.mu_dt = (Real)job.mu_dt;
@@ -142,24 +145,17 @@ static cudaError_t launch_t(const CvaJob &job, const Geometry *geom, int grid, u
             return e;
         }
     }
-    if (geom) {
-        mc_accumulate_kernel<Cva<Real>><<<grid, kThreads, 0, stream>>>(narrow<Real>(job), *geom, d_acc);
-    } else {
-        const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
-        mc_paths_kernel<Cva<Real>><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(
-            narrow<Real>(job), first_unit, n_units, (Real *)d_out);
-    }
+    if (geom)
+        return accumulate_launch<Cva<Real, true>>(grid, narrow<Cva<Real, true>>(job), *geom, d_acc, stream);
+    const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
+    mc_paths_kernel<Cva<Real>><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(
+        narrow<Cva<Real>>(job), first_unit, n_units, (Real *)d_out);
     return cudaGetLastError();
 }
 
 int cva_blocks_per_sm(int precision)
 {
-    int n = 0;
-    cudaError_t e = precision ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                                    &n, mc_accumulate_kernel<Cva<double>>, kThreads, 0)
-                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                                    &n, mc_accumulate_kernel<Cva<float>>, kThreads, 0);
-    return e == cudaSuccess ? n : 0;
+    return precision ? accumulate_blocks_per_sm<Cva<double, true>>() : accumulate_blocks_per_sm<Cva<float, true>>();
 }
 
 cudaError_t cva_launch(int precision, const CvaJob &job, const Geometry &geom, int grid,

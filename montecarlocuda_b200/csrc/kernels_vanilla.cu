@@ -11,10 +11,13 @@
 
 namespace mcb {
 
-template <typename Real>
-static typename Vanilla<Real>::Params narrow(const VanillaJob &job)
+template <typename Real> using VanillaAccum = Vanilla<Real, VanillaTuning<Real>::kMinBlocks, VanillaTuning<Real>::kUnroll, true>;
+
+template <class W>
+static typename W::Params narrow(const VanillaJob &job)
 {
-    typename Vanilla<Real>::Params p;
+    using Real = typename W::Real;
+    typename W::Params p;
     p.keys = job.keys;
     p.a = (Real)job.a;
     p.k = (Real)job.k;
@@ -24,22 +27,15 @@ static typename Vanilla<Real>::Params narrow(const VanillaJob &job)
 
 int vanilla_blocks_per_sm(int precision)
 {
-    int n = 0;
-    cudaError_t e = precision ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                                    &n, mc_accumulate_kernel<Vanilla<double>>, kThreads, 0)
-                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                                    &n, mc_accumulate_kernel<Vanilla<float>>, kThreads, 0);
-    return e == cudaSuccess ? n : 0;
+    return precision ? accumulate_blocks_per_sm<VanillaAccum<double>>() : accumulate_blocks_per_sm<VanillaAccum<float>>();
 }
 
 cudaError_t vanilla_launch(int precision, const VanillaJob &job, const Geometry &geom, int grid,
                            unsigned long long *d_acc, cudaStream_t stream)
 {
     if (precision)
-        mc_accumulate_kernel<Vanilla<double>><<<grid, kThreads, 0, stream>>>(narrow<double>(job), geom, d_acc);
-    else
-        mc_accumulate_kernel<Vanilla<float>><<<grid, kThreads, 0, stream>>>(narrow<float>(job), geom, d_acc);
-    return cudaGetLastError();
+        return accumulate_launch<VanillaAccum<double>>(grid, narrow<VanillaAccum<double>>(job), geom, d_acc, stream);
+    return accumulate_launch<VanillaAccum<float>>(grid, narrow<VanillaAccum<float>>(job), geom, d_acc, stream);
 }
 
 cudaError_t vanilla_paths(int precision, const VanillaJob &job, unsigned long long first_unit,
@@ -48,10 +44,10 @@ cudaError_t vanilla_paths(int precision, const VanillaJob &job, unsigned long lo
     const int grid = (int)((n_units + kThreads - 1) / kThreads < 65535ull ? (n_units + kThreads - 1) / kThreads
                                                                            : 65535ull);
     if (precision)
-        mc_paths_kernel<Vanilla<double>><<<grid, kThreads, 0, stream>>>(narrow<double>(job), first_unit, n_units,
+        mc_paths_kernel<Vanilla<double>><<<grid, kThreads, 0, stream>>>(narrow<Vanilla<double>>(job), first_unit, n_units,
                                                                         (double *)d_out);
     else
-        mc_paths_kernel<Vanilla<float>><<<grid, kThreads, 0, stream>>>(narrow<float>(job), first_unit, n_units,
+        mc_paths_kernel<Vanilla<float>><<<grid, kThreads, 0, stream>>>(narrow<Vanilla<float>>(job), first_unit, n_units,
                                                                        (float *)d_out);
     return cudaGetLastError();
 }

@@ -28,7 +28,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + ARCH
 
 CUDA_UNITS = ["kernels_vanilla.cu", "kernels_basket.cu", "kernels_cva.cu", "kernels_debug.cu", "engine.cu"]
-HEADERS = ["device_common.cuh", "device_math.cuh", "device_math64.cuh", "tables64.inc", "launch.h", "table_lock.h"]
+HEADERS = ["device_common.cuh", "device_math.cuh", "device_math64.cuh", "tables64.inc", "launch.h", "table_lock.h",
+           "workload_vanilla.cuh", "basket_tc.cuh"]
 DROPIN_WIDTHS = (3, 10, 64)
 
 

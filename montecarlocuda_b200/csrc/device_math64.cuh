@@ -25,10 +25,12 @@
 #ifdef MCB_HOST_MATH
 #include <cmath>
 #define MCB_FN static inline
+#define MCB_MEMBER inline
 #define MCB_TABLE static const
 #else
 #include <cuda_runtime.h>
 #define MCB_FN __device__ __forceinline__
+#define MCB_MEMBER __device__ __forceinline__
 #define MCB_TABLE __device__ const
 #endif
 
@@ -84,10 +86,10 @@ struct Tables64 {
     double exp_tab[256];          // 2^(j/256)
     double turn_hi[1024][2];      // { cos, sin } of 2 pi i / 1024
     double turn_lo[1024][2];      // { cos, sin } of 2 pi j / 2^20
-    MCB_FN void log_entry(int i, double &c, double &l) const { c = log_tab[i][0]; l = log_tab[i][1]; }
-    MCB_FN double exp_entry(int j) const { return exp_tab[j]; }
-    MCB_FN void turn_hi_entry(uint32_t i, double &c, double &s) const { c = turn_hi[i][0]; s = turn_hi[i][1]; }
-    MCB_FN void turn_lo_entry(uint32_t j, double &c, double &s) const { c = turn_lo[j][0]; s = turn_lo[j][1]; }
+    MCB_MEMBER void log_entry(int i, double &c, double &l) const { c = log_tab[i][0]; l = log_tab[i][1]; }
+    MCB_MEMBER double exp_entry(int j) const { return exp_tab[j]; }
+    MCB_MEMBER void turn_hi_entry(uint32_t i, double &c, double &s) const { c = turn_hi[i][0]; s = turn_hi[i][1]; }
+    MCB_MEMBER void turn_lo_entry(uint32_t j, double &c, double &s) const { c = turn_lo[j][0]; s = turn_lo[j][1]; }
 };
 
 #ifndef MCB_HOST_MATH
@@ -104,15 +106,15 @@ struct Tables64Rep {
     double exp_rep[256][16];      // [index][replica] 2^(j/256)
     double turn_hi[1024][2];
     double turn_lo[1024][2];
-    MCB_FN void log_entry(int i, double &c, double &l) const
+    MCB_MEMBER void log_entry(int i, double &c, double &l) const
     {
         const double2 v = *reinterpret_cast<const double2 *>(&log_rep[i][threadIdx.x & 7][0]);
         c = v.x;
         l = v.y;
     }
-    MCB_FN double exp_entry(int j) const { return exp_rep[j][threadIdx.x & 15]; }
-    MCB_FN void turn_hi_entry(uint32_t i, double &c, double &s) const { c = turn_hi[i][0]; s = turn_hi[i][1]; }
-    MCB_FN void turn_lo_entry(uint32_t j, double &c, double &s) const { c = turn_lo[j][0]; s = turn_lo[j][1]; }
+    MCB_MEMBER double exp_entry(int j) const { return exp_rep[j][threadIdx.x & 15]; }
+    MCB_MEMBER void turn_hi_entry(uint32_t i, double &c, double &s) const { c = turn_hi[i][0]; s = turn_hi[i][1]; }
+    MCB_MEMBER void turn_lo_entry(uint32_t j, double &c, double &s) const { c = turn_lo[j][0]; s = turn_lo[j][1]; }
 };
 #endif
 

@@ -26,6 +26,10 @@ void hm_sincos20(const uint32_t *k, double *cs, double *sn, long n)
     for (long i = 0; i < n; i++) sincos_turn20(k[i], cs[i], sn[i], tables());
 }
 void hm_neg2log(const double *u, double *out, long n) { for (long i = 0; i < n; i++) out[i] = neg2log_unit(u[i], tables()); }
+void hm_scaled_log(const double *u, double k, double k_ln2, double *out, long n)
+{
+    for (long i = 0; i < n; i++) out[i] = scaled_log_unit(u[i], tables(), k, k_ln2);
+}
 void hm_sqrt(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = sqrt_pos(x[i]); }
 void hm_rcp(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = rcp_newton(x[i]); }
 void hm_exp(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = exp_tab(x[i], tables()); }

@@ -97,6 +97,33 @@ def test_host_build_of_device_math(hostmath):
     check(run)
 
 
+def test_scaled_log_is_the_log_with_the_scale_folded_in(hostmath):
+    """scaled_log_unit(u, k, k ln2) = k ln(u): with k = -2 it IS neg2log_unit, bit for bit; with k = -2 b^2 (the
+    diffusion scale folded under the Box-Muller square root, csrc/device_math.cuh polar_from_words) it stays within a
+    few ulp of the exactly scaled value."""
+    rng = np.random.default_rng(3)
+    u = np.concatenate([2.0 - (1.0 + rng.integers(0, 1 << 44, 200_000) * 2.0 ** -44), [1.0, 2.0 ** -44, 0.5, 0.999999999999]])
+    u = np.ascontiguousarray(u, dtype=np.float64)
+
+    def scaled(k):
+        out = np.empty(len(u))
+        hostmath.hm_scaled_log(C.c_void_p(u.ctypes.data), C.c_double(k), C.c_double(k * 0.69314718055994530942),
+                               C.c_void_p(out.ctypes.data), C.c_long(len(u)))
+        return out
+
+    ref = np.empty(len(u))
+    hostmath.hm_neg2log(C.c_void_p(u.ctypes.data), C.c_void_p(ref.ctypes.data), C.c_long(len(u)))
+    assert np.array_equal(scaled(-2.0), ref)
+    for b in (0.2, 0.2 * 1.4426950408889634, 0.0282842712474619, 1.7):
+        k = -2.0 * b * b
+        want = (k * np.log(u.astype(np.longdouble))).astype(np.float64)
+        err = np.abs(scaled(k) - want)
+        # absolute part: neg2log's 1.25e-16 per unit of |k|, plus the rounding of the constant k ln2 (<= 2^-53 |k ln2|
+        # per unit of exponent; it matters next to u = 1, where e ln2 and -ln c cancel)
+        assert np.all(err <= abs(k) * 2.5e-16 + 4 * 2.0 ** -52 * np.abs(want) + 1e-299), (b, err.max())
+    assert np.all(scaled(0.0) == 1e-300)       # zero volatility: the radius collapses to the guard value
+
+
 @pytest.mark.gpu
 def test_device_math_on_gpu(engine):
     check(lambda fn, x: engine.math64(fn, x))

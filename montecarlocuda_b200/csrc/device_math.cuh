@@ -37,23 +37,29 @@ struct SharedTables64 {
     }
 };
 // the same tables in the bank-conflict-free layout (device_math64.cuh), for the pricing kernels
+__device__ __forceinline__ void load_tables_rep(Tables64Rep &t)
+{
+    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+        t.log_rep[i >> 3][i & 7][0] = kLogTable[i >> 3][0];
+        t.log_rep[i >> 3][i & 7][1] = kLogTable[i >> 3][1];
+    }
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x)
+        t.exp_rep[i >> 4][i & 15] = kExpTable[i >> 4];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        t.turn_hi[i][0] = kTurnHiTable[i][0];
+        t.turn_hi[i][1] = kTurnHiTable[i][1];
+        t.turn_lo[i][0] = kTurnLoTable[i][0];
+        t.turn_lo[i][1] = kTurnLoTable[i][1];
+    }
+}
 struct SharedTables64Rep {
     Tables64Rep t;
-    __device__ __forceinline__ void load()
-    {
-        for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-            t.log_rep[i >> 3][i & 7][0] = kLogTable[i >> 3][0];
-            t.log_rep[i >> 3][i & 7][1] = kLogTable[i >> 3][1];
-        }
-        for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x)
-            t.exp_rep[i >> 4][i & 15] = kExpTable[i >> 4];
-        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-            t.turn_hi[i][0] = kTurnHiTable[i][0];
-            t.turn_hi[i][1] = kTurnHiTable[i][1];
-            t.turn_lo[i][0] = kTurnLoTable[i][0];
-            t.turn_lo[i][1] = kTurnLoTable[i][1];
-        }
-    }
+    __device__ __forceinline__ void load() { load_tables_rep(t); }
+};
+// ... and with the math constants taken from the constant bank (register-capped kernels: CVA)
+struct SharedTables64RepBank {
+    Tables64RepBank t;
+    __device__ __forceinline__ void load() { load_tables_rep(t); }
 };
 template <typename Real> struct SharedFor;
 template <> struct SharedFor<float> { using type = NoShared; };

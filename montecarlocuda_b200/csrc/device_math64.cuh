@@ -41,6 +41,34 @@ namespace hostmath {
 
 #include "tables64.inc"
 
+// Polynomial and reduction constants that do not fit an instruction's immediate field (an fp64 immediate is the
+// high word only).  Written as literals, ptxas re-materialises each use with two MOVs -- in the register-capped CVA
+// kernel that was 38 of the 167 instructions of a path-step (profiles/r01k_cva50_f64_2p26.txt: UMOV 20, IMAD.MOV 12,
+// LDC 6 per step).  From the constant bank they are plain DFMA operands (CVA 20.4 -> 19.8 ms).  Kernels with
+// registers to spare keep the literals: there ptxas holds them in registers across the loop and the constant-bank
+// operands are slower (vanilla fp64 9.72 -> 10.36 ms when forced), so the choice rides on the table type
+// (Tab::kConstBank) the kernel instantiates the functions with.
+struct MathConsts64 {
+    double log_magic;          // 2^52 + 1023
+    double log_c6, log_c5, log_c3;   // -1/6, 1/5, 1/3   (-1/4, -1/2 are immediates)
+    double neg2ln2;            // -2 ln 2
+    double tiny;               // 1e-300
+    double exp_scale;          // 256 / ln 2
+    double exp_ln2_hi, exp_ln2_lo;   // -ln2/256 split (Cody-Waite)
+    double exp_c4, exp_c3;     // 1/24, 1/6
+    double inv_sqrt_2pi;
+    double hast_k, hast_a1, hast_a2, hast_a3, hast_a4, hast_a5;
+};
+#define MCB_MATH_CONSTS_INIT                                                                                             \
+    {4503599627371519.0, -1.0 / 6.0, 0.2, 1.0 / 3.0, -2.0 * 0x1.62e42fefa39efp-1, 1e-300, 0x1.71547652b82fep+8,           \
+     -0x1.62e42fee00000p-9, -0x1.a39ef35793c76p-41, 1.0 / 24.0, 1.0 / 6.0, 0.39894228040143267793994605993438, 0.2316419,   \
+     0.31938153, -0.356563782, 1.781477937, -1.821255978, 1.330274429}
+#ifdef MCB_HOST_MATH
+static const MathConsts64 kMathConsts64 = MCB_MATH_CONSTS_INIT;
+#else
+static __constant__ MathConsts64 kMathConsts64 = MCB_MATH_CONSTS_INIT;
+#endif
+
 // ---- bit access and the two MUFU seeds -----------------------------------------------------------
 #ifdef MCB_HOST_MATH
 MCB_FN int hi_word(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
@@ -81,7 +109,9 @@ MCB_FN double rcp_seed(double x)
 // The tables live in shared memory inside the kernels (random per-thread indices: a constant-bank
 // read would serialise); this is the view the functions take.  Plain layout: host build, instrumentation
 // and per-path kernels.
+#define MCB_K(Tab, field, literal) (Tab::kConstBank ? kMathConsts64.field : (literal))
 struct Tables64 {
+    static constexpr bool kConstBank = false;
     double log_tab[256][2];       // { c_i, -ln c_i }
     double exp_tab[256];          // 2^(j/256)
     double turn_hi[1024][2];      // { cos, sin } of 2 pi i / 1024
@@ -102,6 +132,7 @@ struct Tables64 {
 // or t % 16 (8-byte entries), so threads that are served together can never share a bank.  Same values, same
 // arithmetic, bit-identical results; 64 KB instead of 6 KB, shared by all warps of a (large) CTA.
 struct Tables64Rep {
+    static constexpr bool kConstBank = false;
     double log_rep[256][8][2];    // [index][replica]{ c_i, -ln c_i }
     double exp_rep[256][16];      // [index][replica] 2^(j/256)
     double turn_hi[1024][2];
@@ -115,6 +146,9 @@ struct Tables64Rep {
     MCB_MEMBER double exp_entry(int j) const { return exp_rep[j][threadIdx.x & 15]; }
     MCB_MEMBER void turn_hi_entry(uint32_t i, double &c, double &s) const { c = turn_hi[i][0]; s = turn_hi[i][1]; }
     MCB_MEMBER void turn_lo_entry(uint32_t j, double &c, double &s) const { c = turn_lo[j][0]; s = turn_lo[j][1]; }
+};
+struct Tables64RepBank : Tables64Rep {   // same layout; the functions take their constants from the constant bank
+    static constexpr bool kConstBank = true;
 };
 #endif
 
@@ -143,18 +177,18 @@ template <class Tab> MCB_FN double neg2log_unit(double u, const Tab &T)
     const int idx = (hi >> 12) & 0xff;
     const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(u));
     // exponent as a double without a conversion instruction: 2^52 + biased exponent, minus (2^52 + 1023)
-    const double e = make_double(0x43300000, (int)((unsigned)hi >> 20)) - 4503599627371519.0;
+    const double e = make_double(0x43300000, (int)((unsigned)hi >> 20)) - MCB_K(Tab, log_magic, 4503599627371519.0);
     double c, l;
     T.log_entry(idx, c, l);
     const double r = fma_(m, c, -1.0);
-    double q = fma_(r, -1.0 / 6.0, 0.2);
+    double q = fma_(r, MCB_K(Tab, log_c6, -1.0 / 6.0), MCB_K(Tab, log_c5, 0.2));
     q = fma_(r, q, -0.25);
-    q = fma_(r, q, 1.0 / 3.0);
+    q = fma_(r, q, MCB_K(Tab, log_c3, 1.0 / 3.0));
     q = fma_(r, q, -0.5);
     const double p = fma_(r * r, q, r);                    // log1p(r)
     // -2 (e ln2 + l) + 1e-300: the tiny offset (free: it rides in an FMA) keeps the result away from
     // an exact 0 at u == 1, so the square root below needs no zero guard
-    const double t = fma_(e, -2.0 * 0x1.62e42fefa39efp-1, fma_(l, -2.0, 1e-300));
+    const double t = fma_(e, MCB_K(Tab, neg2ln2, -2.0 * 0x1.62e42fefa39efp-1), fma_(l, -2.0, MCB_K(Tab, tiny, 1e-300)));
     return fma_(p, -2.0, t);
 }
 
@@ -166,16 +200,16 @@ template <class Tab> MCB_FN double scaled_log_unit(double u, const Tab &T, doubl
     const int hi = hi_word(u);
     const int idx = (hi >> 12) & 0xff;
     const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(u));
-    const double e = make_double(0x43300000, (int)((unsigned)hi >> 20)) - 4503599627371519.0;
+    const double e = make_double(0x43300000, (int)((unsigned)hi >> 20)) - MCB_K(Tab, log_magic, 4503599627371519.0);
     double c, l;
     T.log_entry(idx, c, l);
     const double r = fma_(m, c, -1.0);
-    double q = fma_(r, -1.0 / 6.0, 0.2);
+    double q = fma_(r, MCB_K(Tab, log_c6, -1.0 / 6.0), MCB_K(Tab, log_c5, 0.2));
     q = fma_(r, q, -0.25);
-    q = fma_(r, q, 1.0 / 3.0);
+    q = fma_(r, q, MCB_K(Tab, log_c3, 1.0 / 3.0));
     q = fma_(r, q, -0.5);
     const double p = fma_(r * r, q, r);                    // log1p(r)
-    const double t = fma_(e, k_ln2, fma_(l, k, 1e-300));
+    const double t = fma_(e, k_ln2, fma_(l, k, MCB_K(Tab, tiny, 1e-300)));
     return fma_(p, k, t);
 }
 
@@ -249,14 +283,14 @@ MCB_FN void sincos_turn(uint32_t k_hi, uint32_t k_lo, double &cs, double &sn)
 // job's reachable exponent range (engine.cu: make_*_job) and the CVA kernel floors -d^2/2 at -700.
 template <class Tab> MCB_FN double exp_tab(double x, const Tab &T)
 {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    const double t = fma_(x, 0x1.71547652b82fep+8, magic);
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52 (an immediate: low word zero)
+    const double t = fma_(x, MCB_K(Tab, exp_scale, 0x1.71547652b82fep+8), magic);
     const int n = lo_word(t);
     const double nd = t - magic;
-    double r = fma_(nd, -0x1.62e42fee00000p-9, x);
-    r = fma_(nd, -0x1.a39ef35793c76p-41, r);
+    double r = fma_(nd, MCB_K(Tab, exp_ln2_hi, -0x1.62e42fee00000p-9), x);
+    r = fma_(nd, MCB_K(Tab, exp_ln2_lo, -0x1.a39ef35793c76p-41), r);
     const double tj = T.exp_entry(n & 255);
-    double p = fma_(r, 1.0 / 24.0, 1.0 / 6.0);
+    double p = fma_(r, MCB_K(Tab, exp_c4, 1.0 / 24.0), MCB_K(Tab, exp_c3, 1.0 / 6.0));
     p = fma_(r, p, 0.5);
     p = fma_(r * r, p, r);          // e^r - 1
     const double v = fma_(tj, p, tj);

@@ -32,15 +32,25 @@ static TableLock g_cva_lock;
 
 // pdf * polynomial(k), k = 1 / (1 + 0.2316419 |d|): the upper-tail probability of |d|
 // (Abramowitz-Stegun 26.2.17, the constants of DP/MonteCarloKernel.cu:111-116)
-template <typename Real>
+template <typename Real, bool kBank = false>
 __device__ __forceinline__ Real hastings_tail(Real d, Real pdf)
 {
-    const Real k = rcp_real(fma((Real)0.2316419, fabs(d), (Real)1.0));
-    Real poly = fma(k, (Real)1.330274429, (Real)-1.821255978);
-    poly = fma(k, poly, (Real)1.781477937);
-    poly = fma(k, poly, (Real)-0.356563782);
-    poly = fma(k, poly, (Real)0.31938153);
-    return pdf * (k * poly);
+    if constexpr (kBank) {
+        const MathConsts64 &K = kMathConsts64;  // constant-bank operands instead of re-materialised immediates
+        const double k = rcp_real(fma(K.hast_k, fabs(d), 1.0));
+        double poly = fma(k, K.hast_a5, K.hast_a4);
+        poly = fma(k, poly, K.hast_a3);
+        poly = fma(k, poly, K.hast_a2);
+        poly = fma(k, poly, K.hast_a1);
+        return pdf * (k * poly);
+    } else {
+        const Real k = rcp_real(fma((Real)0.2316419, fabs(d), (Real)1.0));
+        Real poly = fma(k, (Real)1.330274429, (Real)-1.821255978);
+        poly = fma(k, poly, (Real)1.781477937);
+        poly = fma(k, poly, (Real)-0.356563782);
+        poly = fma(k, poly, (Real)0.31938153);
+        return pdf * (k * poly);
+    }
 }
 
 // max(a, -700) for a <= 0 without touching the fp64 pipe: negative doubles order like their high
@@ -51,6 +61,14 @@ __device__ __forceinline__ double floor_at_minus_700(double a)
     return __hiloint2double((int)hi, hi == 0xC085E000u ? 0 : __double2loint(a));
 }
 __device__ __forceinline__ float floor_at_minus_700(float a) { return a; }  // MUFU.EX2(-inf) = 0
+
+template <typename Real, bool kBank = false> __device__ __forceinline__ Real inv_sqrt_2pi()
+{
+    if constexpr (kBank)
+        return kMathConsts64.inv_sqrt_2pi;
+    else
+        return (Real)0.39894228040143267793994605993438;
+}
 
 template <typename RealT, bool kAccumLayout = false>
 struct Cva {
@@ -66,7 +84,9 @@ struct Cva {
         PolarScale<Real> scale;  // of sig_dt = v sqrt(dt), folded under the Box-Muller square root
         int n_dates;  // kept dates
     };
-    using Shared = std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>;
+    // fp64 pricing kernel: replicated tables + constant-bank math constants (80-register cap, see device_math64.cuh)
+    static constexpr bool kBank = kAccumLayout && sizeof(RealT) == 8;
+    using Shared = std::conditional_t<kBank, SharedTables64RepBank, typename SharedFor<Real>::type>;
     // one exposure date; the diffusion sig_dt z arrives as (sig_dt r) * (cos or sin) and folds into the step's FMA
     static __device__ __forceinline__ void step(const Params &P, const CvaDate<Real> &D, Real sr, Real trig, Real &y,
                                                 Real &cva, const Shared &sh)
@@ -77,10 +97,10 @@ struct Cva {
         const Real d2 = d1 - D.sig;
         // -d1^2/2 can be -1e14 (a date a few ulps before maturity) or -inf (exact grid, tau = 0):
         // floor it where e^x is already 0 for every purpose, so the table-driven exp stays in range
-        const Real pdf1 = (Real)0.39894228040143267793994605993438 * exp_real(floor_at_minus_700((Real)-0.5 * d1 * d1), sh);
+        const Real pdf1 = inv_sqrt_2pi<Real, kBank>() * exp_real(floor_at_minus_700((Real)-0.5 * d1 * d1), sh);
         const Real pdf2 = pdf1 * s * D.rkd;
-        const Real t1 = hastings_tail(d1, pdf1);
-        const Real t2 = hastings_tail(d2, pdf2);
+        const Real t1 = hastings_tail<Real, kBank>(d1, pdf1);
+        const Real t2 = hastings_tail<Real, kBank>(d2, pdf2);
         const Real n1 = d1 > 0 ? (Real)1.0 - t1 : t1;
         const Real n2 = d2 > 0 ? (Real)1.0 - t2 : t2;
         const Real ee = s * n1 - D.kd * n2;

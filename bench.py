@@ -47,6 +47,15 @@ WORKLOADS = {
     "basket64_f32_2p30": dict(kind="basket", n=64, prec="f32", paths=1 << 30, bound="issue", work=3236.0, units_per_path=1),
 }
 PIPE_PER_CLK_PER_SM = {"fp64": 64.0, "mufu": 16.0, "issue": 128.0}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the workload's kernel at the full path count, from the
+# `ncu --set full` captures summarised under profiles/ (bytes, source file): the path has no HBM-resident data
+DRAM_TRAFFIC = {
+    "vanilla_f64_2p32": (70_400, "profiles/r01k_vanilla_f64_2p32.txt"),
+    "vanilla_f32_2p32": (18_944, "profiles/r01j_vanilla_f32_2p32.txt"),
+    "basket10_f64_2p28": (72_192, "profiles/r01k_basket10_f64_2p28.txt"),
+    "cva50_f64_2p26": (99_072, "profiles/r01k_cva50_f64_2p26.txt"),
+    "basket64_f32_2p30": (120_832, "profiles/r01j_basket64_f32_2p30_tensor.txt"),
+}
 HEADLINE = "vanilla_f64_2p32"
 
 
@@ -302,7 +311,7 @@ def param_bytes(w):
     return 8 * (4 * n + n * n + 3)
 
 
-def roofline(w, value, clocks):
+def roofline(w, value, clocks, name=None):
     peaks = measured_peaks()
     f_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
     pipe = PIPE_PER_CLK_PER_SM[w["bound"]]
@@ -315,6 +324,8 @@ def roofline(w, value, clocks):
     f_run = (clocks or {}).get("sm_mhz")
     if f_run:
         out["frac_at_sampled_clock"] = achieved / (pipe * SM_COUNT * f_run * 1e6)
+    if name in DRAM_TRAFFIC:
+        out["traffic"], out["traffic_source"] = DRAM_TRAFFIC[name][0], DRAM_TRAFFIC[name][1] + " (bytes per launch, 1 GPU, whole job)"
     return out
 
 
@@ -360,7 +371,7 @@ def main():
         ww = WORKLOADS[name]
         r = time_workload(name, ww, pricer, dist, torch, rank, world, max(2, args.steps // 2), 3, sample_clocks=(rank == 0), gpu_index=local)
         also[name] = {"value": r["value"], "unit": unit_name(ww), "ms_per_step": r["ms_per_step"], "e2e": r["e2e_value"],
-                      "dtype": ww["prec"], "roofline": roofline(ww, r["value"] / world, r["clocks"]),
+                      "dtype": ww["prec"], "roofline": roofline(ww, r["value"] / world, r["clocks"], name),
                       "price": r["result"].Expected, "std_error": r["result"].std_error, "clocks": r["clocks"]}
 
     if rank == 0:
@@ -374,7 +385,7 @@ def main():
                        ("fused into the pricing kernel: last CTA pushes 96 bytes to every peer mailbox over NVLink and adds the peers' limbs (no separate collective)"
                         if pricer.combine == "peer" else "one int64 SUM all-reduce (NCCL) of 96 bytes per step" + (f" [{pricer.combine_note}]" if pricer.combine_note else "")),
                        "l2": "not applicable: compute-bound, no resident input (parameters <= 33 KB in the constant bank, output 96 bytes)"},
-            "roofline": roofline(w, main_run["value"] / world, main_run["clocks"]),
+            "roofline": roofline(w, main_run["value"] / world, main_run["clocks"], args.workload),
             "e2e": {"value": main_run["e2e_value"], "unit": unit_name(w), "h2d_bytes_per_step": main_run["params_bytes"] + 208,
                     "d2h_bytes_per_step": 96, "api": "mcb200_vanilla/basket/cva (blocking C-ABI call, host structs in, result out)" if world == 1
                     else "ShardedPricer.price per rank (launch + cross-GPU combine + read-back + closing)"},

@@ -121,3 +121,22 @@ def test_finalize_is_the_reference_closing(ensure_built, oracle):
     acc_bad[11] = 1                       # overflow / NaN flag
     with pytest.raises(m.Mcb200Error):
         m.finalize(p, acc_bad)
+
+
+def test_peer_and_engine_switch_argument_checks(ensure_built):
+    """Host-side validation of the additive entry points (no device needed): the peer-group API
+    (include/mcb200.h, the fused cross-GPU combine) and the basket engine switch."""
+    from montecarlocuda_b200 import _lib
+    lib = _lib.load()
+    handle = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+    peer = C.c_void_p()
+    assert lib.mcb200_peer_create(None, 0, 2, C.byref(peer), handle) == _lib.ERR_INVALID
+    assert lib.mcb200_peer_connect(None, handle) == _lib.ERR_INVALID
+    assert lib.mcb200_peer_connect_local(None, 2) == _lib.ERR_INVALID
+    assert lib.mcb200_peer_attach(None, None) == _lib.ERR_INVALID
+    assert lib.mcb200_peer_destroy(None) == _lib.OK
+    before = lib.mcb200_get_basket_engine()
+    assert before in (0, 1)
+    assert lib.mcb200_set_basket_engine(2) == _lib.ERR_INVALID and lib.mcb200_get_basket_engine() == before
+    assert lib.mcb200_set_basket_engine(1) == _lib.OK and lib.mcb200_get_basket_engine() == 1
+    assert lib.mcb200_set_basket_engine(before) == _lib.OK

@@ -355,6 +355,49 @@ def test_full_size_vanilla_fp32_2pow32(engine):
     assert r.std_error < 2.5e-4
 
 
+def test_full_size_vanilla_fp64_2pow32(engine):
+    """BASELINE config 2, fp64 (the headline): 2^32 paths within 3 SE of closed-form Black-Scholes (north_star)."""
+    r = engine.vanilla(VAN, 1 << 32, "f64")
+    assert r.n_paths == 1 << 32
+    assert abs(r.Expected - BS_EXACT) < 3 * r.std_error and r.std_error < 2.5e-4
+
+
+def test_full_size_cva_fp64_2pow26(engine, oracle):
+    """BASELINE config 4: CVA, 50 exposure dates, 2^26 paths fp64: within 3 SE (1.7e-5) of the closed form
+    E[CVA] = LGD C0 sum_j dp_j e^{r t_j} over the dates the reference's fp64 grid keeps."""
+    r = engine.cva(CVA50, 1 << 26, "f64")
+    _, keep = oracle.cva_grid(1.0, 50, "f64")
+    closed = oracle.cva_closed_form(100, 100, 0.05, 0.2, 1.0, 0.03, 0.6, 50, keep)
+    assert r.n_paths == 1 << 26
+    assert abs(r.Expected - closed) < 3 * r.std_error + 1e-6     # + the Hastings cnd's own bias
+    assert 1.5e-5 < r.std_error < 2.0e-5
+
+
+def test_full_size_baskets_agree_across_precisions_and_engines(engine, oracle):
+    """BASELINE configs 3 and 5 at full size.  No closed form exists for a basket: the anchors are the golden
+    reference host runs (tests above) and, here, agreement between independent code paths on the full job:
+    N=10 fp64 (2^28 paths) against its fp32 kernel, N=64 fp32 (2^30 paths) tensor-core engine against the FFMA
+    engine -- same Philox positions, different arithmetic -- within 3 combined standard errors."""
+    b10 = make_basket(oracle, 10)
+    d = engine.basket(b10, 1 << 28, "f64")
+    f = engine.basket(make_basket(oracle, 10, "f32"), 1 << 28, "f32")
+    assert d.n_paths == f.n_paths == 1 << 28
+    assert abs(d.Expected - f.Expected) < 3 * np.hypot(d.std_error, f.std_error)
+    assert 8.5 < d.Expected < 8.8 and d.std_error < 8e-4
+    b64 = make_basket(oracle, 64, "f32")
+    m.set_basket_engine(m.BASKET_TENSOR)
+    t = engine.basket(b64, 1 << 30, "f32")
+    m.set_basket_engine(m.BASKET_FFMA)
+    try:
+        g = engine.basket(b64, 1 << 30, "f32")
+    finally:
+        m.set_basket_engine(m.BASKET_TENSOR)
+    assert t.n_paths == g.n_paths == 1 << 30
+    # the same paths with different rounding: far closer than the Monte Carlo error (3.2e-4)
+    assert abs(t.Expected - g.Expected) < 0.1 * t.std_error
+    assert 8.0 < t.Expected < 8.3 and t.std_error < 4e-4
+
+
 def test_linearity_in_notional(engine):
     # payoff is positively homogeneous: scaling S0 and K by 2 (an exact power of two) scales every path
     # value by exactly 2, so sum doubles and sumsq quadruples bit for bit (fp64 and the limb split are

@@ -45,19 +45,27 @@ def _launch(engine: Engine, workload: str, p: _lib.PlanT, params, seed: int, fir
 
 class PeerGroup:
     """This rank's membership of a peer-memory combine group, attached to an Engine.  `exchange` turns this
-    rank's 64-byte mailbox handle into the list of all ranks' handles (any transport: here torch.distributed)."""
+    rank's 64-byte mailbox handle into the list of all ranks' handles (any transport: here torch.distributed).
+    Every rank calls exchange() exactly once, whatever happens locally (a rank whose mailbox could not be created
+    contributes an empty handle), so a local failure cannot leave the others waiting in the collective."""
 
     def __init__(self, engine: Engine, rank: int, world: int, exchange):
         self.engine, self.rank, self.world = engine, rank, world
         lib = engine._lib
         self._peer = C.c_void_p()
         handle = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
-        _lib.check(lib.mcb200_peer_create(engine.handle, rank, world, C.byref(self._peer), handle), engine.handle)
-        handles = exchange(bytes(handle))
+        status = lib.mcb200_peer_create(engine.handle, rank, world, C.byref(self._peer), handle)
+        handles = exchange(bytes(handle) if status == _lib.OK else b"")
+        _lib.check(status, engine.handle)
         if len(handles) != world or any(len(h) != _lib.PEER_HANDLE_BYTES for h in handles):
-            raise ValueError("exchange() must return one 64-byte handle per rank")
+            self.close()
+            raise _lib.Mcb200Error(_lib.ERR_CUDA, "a peer rank could not create its mailbox")
         blob = (C.c_ubyte * (_lib.PEER_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
-        _lib.check(lib.mcb200_peer_connect(self._peer, blob), engine.handle)
+        status = lib.mcb200_peer_connect(self._peer, blob)
+        if status != _lib.OK:
+            msg = lib.mcb200_last_error(engine.handle).decode()
+            self.close()
+            raise _lib.Mcb200Error(status, msg or "mcb200_peer_connect failed")
         self.attach()
 
     def attach(self):
@@ -114,22 +122,26 @@ class ShardedPricer:
             raise ValueError("combine must be 'auto', 'peer' or 'nccl'")
         self.combine = "nccl"
         if world > 1 and combine in ("auto", "peer"):
+            import torch.distributed as dist
+            failure = None
             try:
                 with torch.cuda.device(self.device):
                     self.peers = PeerGroup(self.engine, rank, world, _exchange_over_process_group(self.group))
                 self.combine = "peer"
             except Exception as exc:  # mapping peer memory can be refused by the platform (IPC disabled, no P2P)
-                if combine == "peer":
-                    raise
-                self.combine_note = f"peer mailboxes unavailable ({exc}); using the NCCL all-reduce"
-            # every rank must take the same route
-            import torch.distributed as dist
+                failure = exc
+            # every rank must take the same route: agree before anybody raises or falls back
             flag = torch.tensor([1 if self.combine == "peer" else 0], dtype=torch.int32, device=self.device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-            if int(flag.item()) == 0 and self.combine == "peer":
-                self.peers.detach()
+            if int(flag.item()) == 0:
+                if self.peers is not None:
+                    self.peers.close()
+                    self.peers = None
                 self.combine = "nccl"
-                self.combine_note = "a peer rank could not map the mailboxes; using the NCCL all-reduce"
+                self.combine_note = (f"peer mailboxes unavailable ({failure}); using the NCCL all-reduce" if failure is not None
+                                     else "a peer rank could not map the mailboxes; using the NCCL all-reduce")
+                if combine == "peer":
+                    raise RuntimeError(self.combine_note.replace("; using the NCCL all-reduce", ""))
 
     def _world(self):
         import torch.distributed as dist

@@ -168,7 +168,7 @@ template <class Tab>
 __device__ __forceinline__ void box_muller_f64(uint32_t wa, uint32_t wb, double &z0, double &z1, const Tab &T)
 {
     const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
-    const double r = sqrt_pos(fabs(neg2log_unit(2.0 - f, T)));
+    const double r = sqrt_pos<true>(fabs(neg2log_unit(2.0 - f, T)));
     double cs, sn;
     sincos_turn20(wb & 0x000fffffu, cs, sn, T);
     z0 = r * cs;
@@ -203,6 +203,7 @@ template <typename Real> __host__ __device__ inline PolarScale<Real> polar_scale
     }
     return s;
 }
+template <bool kShortSqrt = false>
 __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], float (&br)[3], float (&cs)[3], float (&sn)[3],
                                                  const NoShared &, const PolarScale<float> &S)
 {
@@ -216,7 +217,7 @@ __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], float (
         sn[i] = mufu_sin(ang);
     }
 }
-template <class Sh>
+template <bool kShortSqrt = false, class Sh>
 __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], double (&br)[2], double (&cs)[2], double (&sn)[2],
                                                  const Sh &sh, const PolarScale<double> &S)
 {
@@ -224,7 +225,7 @@ __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], double 
     for (int i = 0; i < 2; i++) {
         const uint32_t wa = w[2 * i], wb = w[2 * i + 1];
         const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
-        br[i] = sqrt_pos(fabs(scaled_log_unit(2.0 - f, sh.t, S.c, S.c_ln2)));
+        br[i] = sqrt_pos<kShortSqrt>(fabs(scaled_log_unit(2.0 - f, sh.t, S.c, S.c_ln2)));
         sincos_turn20(wb & 0x000fffffu, cs[i], sn[i], sh.t);
     }
 }

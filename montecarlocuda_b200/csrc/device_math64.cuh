@@ -4,7 +4,7 @@
 // integer ones (measured: 162 warp-instructions per vanilla path, profiles/r01a_*).  Here:
 //
 //   neg2log_unit   -2 ln(u), u in (0,1]   table of 256 reciprocals (shared memory) + degree-6 log1p   9 fp64
-//   sqrt_pos       sqrt(x)                MUFU.RSQ64H seed + 2 coupled Newton steps                   7 fp64
+//   sqrt_pos       sqrt(x)                MUFU.RSQ64H seed + 2 coupled Newton steps (or 1 + a correction) 7 / 5 fp64
 //   sincos_turn    cos/sin(2 pi k/2^52)   octant taken from the integer bits (exact reduction),
 //                                         fdlibm kernel polynomials on [0, pi/4]                     18 fp64
 //   exp_tab        e^x                    n = rint(256 x / ln2) by magic add, Cody-Waite, table of
@@ -214,12 +214,27 @@ template <class Tab> MCB_FN double scaled_log_unit(double u, const Tab &T, doubl
 }
 
 // ---- sqrt(x), x > 0 finite and normal ------------------------------------------------------------
-// y ~ 1/sqrt(x) to 2^-22; g = x y, h = y/2; two coupled Newton steps r = 1/2 - h g; g += g r; h += h r.
-// No zero guard: the only caller feeds |neg2log_unit| >= 1e-300.
-MCB_FN double sqrt_pos(double x)
+// y ~ 1/sqrt(x) to 2^-22 (MUFU.RSQ64H); g = x y, h = y/2.
+//   kShort = false: two coupled Newton steps r = 1/2 - h g; g += g r; h += h r (7 fp64 instructions; g and h
+//                   update side by side).
+//   kShort = true:  one coupled step brings g to 1.5 * 2^-44; the Newton correction g += (x - g^2) h only needs h
+//                   to the seed's accuracy (error 2^-44 * 2^-22), so h is never refined and y/2 is an exponent
+//                   decrement on the integer pipe: 5 fp64 instructions.
+// Both are within 1 ulp (tests/test_device_math64.py).  Which one is faster depends on the kernel around it
+// (measured, profiles/r01j_tune_vanilla.txt): the European call runs 3 % FASTER with the longer version (its two
+// independent update chains schedule better between the table look-ups), the basket and CVA kernels 1.5-2 % faster
+// with the short one.  No zero guard: the only callers feed |k ln u| >= 1e-300.
+template <bool kShort = false> MCB_FN double sqrt_pos(double x)
 {
     const double y = rsqrt_seed(x);
     double g = x * y;
+    if (kShort) {
+        const double h = make_double(hi_word(y) - 0x00100000, lo_word(y));   // y / 2
+        const double r = fma_(-h, g, 0.5);
+        g = fma_(g, r, g);
+        const double d = fma_(-g, g, x);
+        return fma_(d, h, g);
+    }
     double h = 0.5 * y;
     double r = fma_(-h, g, 0.5);
     g = fma_(g, r, g);

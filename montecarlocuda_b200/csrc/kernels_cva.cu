@@ -116,7 +116,7 @@ struct Cva {
             uint32_t w[4];
             philox4x32_10(path_lo, path_hi, (uint32_t)jb, kTagCva, P.keys, w);
             Real sr[kNpb / 2], cs[kNpb / 2], sn[kNpb / 2];
-            polar_from_words(w, sr, cs, sn, sh, P.scale);
+            polar_from_words<true>(w, sr, cs, sn, sh, P.scale);
 #pragma unroll
             for (int q = 0; q < kNpb; q++) {
                 const int j = jb * kNpb + q;

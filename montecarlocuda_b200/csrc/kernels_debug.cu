@@ -91,6 +91,7 @@ __global__ void debug_math64_kernel(int fn, unsigned long long n, const double *
         switch (fn) {
             case 0: a = neg2log_unit(x, sh.t); break;
             case 1: a = sqrt_pos(x); break;
+            case 6: a = sqrt_pos<true>(x); break;
             case 2: a = rcp_newton(x); break;
             case 3: a = exp_tab(x, sh.t); break;
             case 4: sincos_turn((uint32_t)__double2hiint(x), (uint32_t)__double2loint(x), a, b); break;

@@ -31,6 +31,7 @@ void hm_scaled_log(const double *u, double k, double k_ln2, double *out, long n)
     for (long i = 0; i < n; i++) out[i] = scaled_log_unit(u[i], tables(), k, k_ln2);
 }
 void hm_sqrt(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = sqrt_pos(x[i]); }
+void hm_sqrt_short(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = sqrt_pos<true>(x[i]); }
 void hm_rcp(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = rcp_newton(x[i]); }
 void hm_exp(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = exp_tab(x[i], tables()); }
 void hm_sincos(const uint32_t *k_hi, const uint32_t *k_lo, double *cs, double *sn, long n)

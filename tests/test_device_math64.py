@@ -42,6 +42,7 @@ def check(run):
     assert ulps(edge, np.exp(np.array([-700.0, 700.0, 0.0]))).max() <= 2
     assert np.isnan(run(3, np.array([np.nan]))[0, 0])
     assert ulps(run(1, c["sqrt"])[:, 0], np.sqrt(c["sqrt"])).max() <= 2
+    assert ulps(run(6, c["sqrt"])[:, 0], np.sqrt(c["sqrt"])).max() <= 2      # short iteration (basket, CVA kernels)
     assert ulps(run(2, c["rcp"])[:, 0], 1.0 / c["rcp"]).max() <= 2
     got = run(0, c["u"])[:, 0]
     want = (-2 * np.log(c["u"].astype(np.longdouble))).astype(np.float64)
@@ -70,7 +71,7 @@ def hostmath(tmp_path_factory):
 
 
 def test_host_build_of_device_math(hostmath):
-    names = {0: "hm_neg2log", 1: "hm_sqrt", 2: "hm_rcp", 3: "hm_exp"}
+    names = {0: "hm_neg2log", 1: "hm_sqrt", 2: "hm_rcp", 3: "hm_exp", 6: "hm_sqrt_short"}
 
     def run(fn, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

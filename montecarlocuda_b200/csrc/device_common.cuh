@@ -27,11 +27,13 @@ struct PhiloxKeys {
 // Peer-memory combine fused into the pricing kernel (multi-GPU, one process per GPU or one process for all).
 // Every rank owns a small mailbox in its device memory that its peers can write over NVLink (CUDA IPC /
 // peer access); mail[r] is rank r's mailbox as addressed from THIS device.  Slot (seq % kPeerRing, src) holds
-// src's 12 accumulator words and, in word kPeerFlagWord, the sequence number that publishes them.
+// src's 12 accumulator words as 24 "flagged halves": every 8-byte mailbox word is {low: 32 bits of data, high: the
+// launch's flag}, written by ONE 8-byte store (atomic), so a word is valid exactly when its flag matches -- no
+// fence, no separate "ready" flag and no second NVLink round trip (the LL protocol of NCCL).
 constexpr int kPeerMax = 8;
 constexpr int kPeerRing = 4;
-constexpr int kPeerSlotWords = 16;
-constexpr int kPeerFlagWord = 12;
+constexpr int kPeerHalves = 2 * kAccWords;   // 24 flagged halves per (slot, source)
+constexpr int kPeerSlotWords = 32;           // 24 used, padded to 256 bytes
 constexpr size_t kPeerMailboxBytes = (size_t)kPeerRing * kPeerMax * kPeerSlotWords * sizeof(unsigned long long);
 struct PeerLink {
     int world;                            // <= 1: no combine, the kernel leaves this device's partial in acc
@@ -177,20 +179,10 @@ __device__ __forceinline__ void scratch_flush(const BlockScratch &sc, unsigned l
 // The (sum, sum^2) combine across GPUs is 96 bytes: as a separate NCCL all-reduce it costs a kernel launch
 // and ~20-30 us of latency after a pricing kernel that, sharded over 8 GPUs, runs for 0.5-10 ms.  Here the
 // LAST CTA of each device's pricing kernel pushes the device's limbs straight into every peer's mailbox
-// (12 x 8-byte stores per peer over NVLink, then a release flag), waits for the peers' flags and adds the
+// (24 flagged 8-byte stores per peer over NVLink), polls its own mailbox for the peers' and adds the
 // integer limbs: when the kernel ends, acc holds the JOB's totals on every rank, bit-identical everywhere
 // (integer addition; the order of arrival cannot matter).  Slot reuse is safe with a ring of 2 or more: a rank
 // cannot finish step s + 1 before every peer has pushed step s + 1, which each peer does after reading step s.
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
 {
     unsigned long long v;
@@ -206,6 +198,7 @@ __device__ __forceinline__ void peer_combine(unsigned long long *acc, const Peer
 {
     __shared__ bool s_last;
     __shared__ unsigned int s_late;
+    __shared__ unsigned int s_half[kPeerMax * kPeerHalves];
     __threadfence();  // this CTA's atomics on acc are ordered before its ticket
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -221,31 +214,35 @@ __device__ __forceinline__ void peer_combine(unsigned long long *acc, const Peer
     if (tid == 0)
         *L.ticket = 0u;  // ready for the next launch on this device (stream order)
     const size_t slot = (size_t)(L.seq % kPeerRing) * kPeerMax;
-    if (tid < kAccWords * L.world) {
-        const int dst = tid / kAccWords, w = tid % kAccWords;
-        const unsigned long long v = *((volatile unsigned long long *)acc + w);
-        st_relaxed_sys(L.mail[dst] + (slot + L.rank) * kPeerSlotWords + w, v);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < L.world) {
-        st_release_sys(L.mail[tid] + (slot + L.rank) * kPeerSlotWords + kPeerFlagWord, L.seq);
-        // wait for rank tid's words.  Bounded: a peer that never launches must end as an error flag, not a hang.
-        const unsigned long long *flag = L.mail[L.rank] + (slot + tid) * kPeerSlotWords + kPeerFlagWord;
+    // never 0 (fresh mailbox memory) and different from the flag this slot carried kPeerRing launches ago
+    const unsigned long long flag = ((unsigned long long)((unsigned int)L.seq | 0x80000000u)) << 32;
+    if (tid < kPeerHalves * L.world) {
+        const int peer = tid / kPeerHalves, h = tid % kPeerHalves;
+        // push: half h of this device's accumulator into rank `peer`'s mailbox
+        const unsigned long long word = *((volatile unsigned long long *)acc + (h >> 1));
+        const unsigned long long half = (h & 1) ? (word >> 32) : (word & 0xffffffffull);
+        st_relaxed_sys(L.mail[peer] + (slot + L.rank) * kPeerSlotWords + h, flag | half);
+        // pull: half h of rank `peer`'s accumulator from this device's mailbox.  Bounded: a peer that never
+        // launches must end as an error flag, not as a hung device.
+        const unsigned long long *src = L.mail[L.rank] + (slot + peer) * kPeerSlotWords + h;
+        unsigned long long v = 0ull;
         bool ok = false;
         for (int spin = 0; spin < (1 << 22) && !ok; spin++) {
-            ok = ld_acquire_sys(flag) == L.seq;
+            v = ld_relaxed_sys(src);
+            ok = (v & 0xffffffff00000000ull) == flag;
             if (!ok)
                 __nanosleep(64);
         }
         if (!ok)
             atomicAdd(&s_late, 1u);
+        s_half[tid] = (unsigned int)v;
     }
     __syncthreads();
     if (tid < kAccWords) {
         unsigned long long total = 0ull;
         for (int src = 0; src < L.world; src++)
-            total += ld_relaxed_sys(L.mail[L.rank] + (slot + src) * kPeerSlotWords + tid);
+            total += (unsigned long long)s_half[src * kPeerHalves + 2 * tid] |
+                     ((unsigned long long)s_half[src * kPeerHalves + 2 * tid + 1] << 32);
         if (tid == kAccWords - 1 && s_late)
             total += 1ull;  // error flag: a peer did not answer
         acc[tid] = total;
@@ -271,7 +268,7 @@ __device__ __forceinline__ void finish(const BlockScratch &sc, unsigned long lon
 //                      part of the first two Philox rounds that depends only on it runs on the uniform datapath
 // A CTA walks chunks first_chunk + blockIdx.x, + gridDim.x, ...; thread t of a chunk owns units
 // base + k * 256 + t for k < rounds, in that order, and accumulates value and value^2 in W::Real
-// (short runs: at most rounds * kUnitPaths <= 256 terms) before the fp64 block reduction.
+// (short runs: at most rounds * kUnitPaths <= 384 terms) before the fp64 block reduction.
 template <class W>
 __global__ void __launch_bounds__(kThreads * W::kSubBlocks, W::kMinBlocks)
 mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_constant__ Geometry G,

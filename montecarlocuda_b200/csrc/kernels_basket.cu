@@ -136,6 +136,40 @@ struct SharedFactor : NoShared {
     }
 };
 
+// The fp64 counterpart, on top of the (replicated) math tables.  Through the constant bank ptxas hoists the
+// loop-invariant factor loads of a 10-asset basket out of the path loop into uniform registers, runs out of
+// them and shuffles the overflow between uniform and vector registers once per path (52 R2UR + ~40 MOV per path,
+// profiles/r01k_basket10_f64_2p28.txt).  From shared memory two entries arrive per (broadcast, conflict-free)
+// 16-byte load right where their DFMAs are.
+template <int kDoubles>
+struct SharedFactor64 : SharedTables64Rep {
+    __align__(16) double factor[kDoubles];
+    __device__ __forceinline__ void load()
+    {
+        SharedTables64Rep::load();
+        const double *src = reinterpret_cast<const double *>(mcb_basket_table);
+        for (int i = threadIdx.x; i < kDoubles; i += blockDim.x)
+            factor[i] = src[i];
+    }
+};
+// xa, xb += {2 consecutive factor entries at smem address base + kByteOffset} * z
+template <int kByteOffset>
+__device__ __forceinline__ void fma_pair_shared_f64(double &xa, double &xb, double z, uint32_t base)
+{
+    asm volatile(
+        "{\n\t.reg .f64 fa, fb;\n\tld.shared.v2.f64 {fa, fb}, [%3+%4];\n\t"
+        "fma.rn.f64 %0, fa, %2, %0;\n\tfma.rn.f64 %1, fb, %2, %1;\n\t}"
+        : "+d"(xa), "+d"(xb)
+        : "d"(z), "r"(base), "n"(kByteOffset));
+}
+template <int kByteOffset>
+__device__ __forceinline__ void fma_one_shared_f64(double &xa, double z, uint32_t base)
+{
+    asm volatile("{\n\t.reg .f64 fa;\n\tld.shared.f64 fa, [%2+%3];\n\tfma.rn.f64 %0, fa, %1, %0;\n\t}"
+                 : "+d"(xa)
+                 : "d"(z), "r"(base), "n"(kByteOffset));
+}
+
 // x2a, x2b += {4 consecutive factor entries at smem address base + kByteOffset} * {z, z}
 template <int kByteOffset>
 __device__ __forceinline__ void packed_fma_quad(unsigned long long &x2a, unsigned long long &x2b, unsigned long long zz,
@@ -170,8 +204,12 @@ struct Basket {
         PhiloxKeys keys;
     };
     static constexpr bool kSharedFactor = Table::kSharedFactor;
-    using Shared = std::conditional_t<kSharedFactor, SharedFactor<(kSharedFactor ? Table::kFactor : 1)>,
-                                      std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>>;
+    // fp64 pricing kernels from 8 assets up read the factor from shared memory too (see SharedFactor64)
+    static constexpr bool kSharedFactor64 = kAccumLayout && sizeof(RealT) == 8 && N >= 8 && N <= 16;  // wider: ptxas spills more than it saves
+    using Shared = std::conditional_t<
+        kSharedFactor, SharedFactor<(kSharedFactor ? Table::kFactor : 1)>,
+        std::conditional_t<kSharedFactor64, SharedFactor64<(kSharedFactor64 ? Table::kFactor : 1)>,
+                           std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>>>;
     template <class Sh> static __device__ __forceinline__ Real grow(Real x, const Sh &sh)
     {
         if constexpr (sizeof(Real) == 4)
@@ -201,11 +239,28 @@ struct Basket {
                                                                   base),
          ...);
     }
+    // fp64 column from shared memory: rows first .. N-1 of column J; 16-byte loads where the entry index is even
+    template <int J, int kRow>
+    static __device__ __forceinline__ void column_shared_f64(State &st, double z, uint32_t base)
+    {
+        if constexpr (kRow < N) {
+            constexpr int idx = Table::index(J, kRow);
+            if constexpr (idx % 2 == 0 && kRow + 1 < N) {
+                fma_pair_shared_f64<idx * 8>(st.x[kRow], st.x[kRow + 1], z, base);
+                column_shared_f64<J, kRow + 2>(st, z, base);
+            } else {
+                fma_one_shared_f64<idx * 8>(st.x[kRow], z, base);
+                column_shared_f64<J, kRow + 1>(st, z, base);
+            }
+        }
+    }
     template <int J, int... kRow>
     static __device__ __forceinline__ void column(State &st, Real z, const Shared &sh, std::integer_sequence<int, kRow...>)
     {
         constexpr int first = Table::first_row(J);
-        if constexpr (kSharedFactor) {
+        if constexpr (kSharedFactor64) {
+            column_shared_f64<J, first>(st, z, (uint32_t)__cvta_generic_to_shared(sh.factor));
+        } else if constexpr (kSharedFactor) {
             constexpr int pairs = sizeof...(kRow);
             const unsigned long long zz = pack2(z, z);
             const uint32_t base = (uint32_t)__cvta_generic_to_shared(sh.factor);

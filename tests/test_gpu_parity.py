@@ -258,6 +258,20 @@ def test_accumulator_matches_oracle_restatement(engine, oracle):
     assert np.array_equal(acc[0], oracle.accumulate(vals, p))
 
 
+@pytest.mark.parametrize("workload,n_assets,prec", [("basket", 10, "f64"), ("basket", 16, "f64"), ("basket", 8, "f64"), ("basket", 3, "f64"),
+                                                    ("basket", 10, "f32"), ("basket", 64, "f64"), ("cva", 0, "f64"), ("cva", 0, "f32")])
+def test_pricing_kernels_sum_exactly_their_path_kernels_values(engine, oracle, workload, n_assets, prec):
+    """The pricing kernels run a different memory layout from the per-path kernels the oracle is compared with
+    (bank-conflict-free replicated fp64 tables, sub-block CTAs, the fp64 factor in shared memory, math constants from
+    the constant bank) but the SAME arithmetic: the accumulator of a job equals, bit for bit, the oracle's restatement
+    of the chunk reduction applied to the per-path kernel's values."""
+    params = make_basket(oracle, n_assets, prec) if workload == "basket" else CVA50
+    n = 40_000 if n_assets < 64 else 9_000
+    p, acc = _shard_accumulators(engine, workload, params, n, prec, 5, 1)
+    vals = getattr(engine, workload + "_paths")(params, 0, n, prec, 5)
+    assert np.array_equal(acc[0], oracle.accumulate(vals, p))
+
+
 # ------------------------------------------------------------------------------------------------
 # the drop-in libraries: the reference's symbols, struct layouts and semantics
 # ------------------------------------------------------------------------------------------------

@@ -50,11 +50,11 @@ PIPE_PER_CLK_PER_SM = {"fp64": 64.0, "mufu": 16.0, "issue": 128.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the workload's kernel at the full path count, from the
 # `ncu --set full` captures summarised under profiles/ (bytes, source file): the path has no HBM-resident data
 DRAM_TRAFFIC = {
-    "vanilla_f64_2p32": (70_400, "profiles/r01k_vanilla_f64_2p32.txt"),
-    "vanilla_f32_2p32": (18_944, "profiles/r01j_vanilla_f32_2p32.txt"),
-    "basket10_f64_2p28": (72_192, "profiles/r01k_basket10_f64_2p28.txt"),
-    "cva50_f64_2p26": (99_072, "profiles/r01k_cva50_f64_2p26.txt"),
-    "basket64_f32_2p30": (120_832, "profiles/r01j_basket64_f32_2p30_tensor.txt"),
+    "vanilla_f64_2p32": (69_120, "profiles/r01n_vanilla_f64_2p32.txt"),
+    "vanilla_f32_2p32": (17_920, "profiles/r01n_vanilla_f32_2p32.txt"),
+    "basket10_f64_2p28": (118_528, "profiles/r01n_basket10_f64_2p28.txt"),
+    "cva50_f64_2p26": (87_296, "profiles/r01n_cva50_f64_2p26.txt"),
+    "basket64_f32_2p30": (124_160, "profiles/r01n_basket64_f32_2p30_tensor.txt"),
 }
 HEADLINE = "vanilla_f64_2p32"
 

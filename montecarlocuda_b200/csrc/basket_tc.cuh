@@ -21,14 +21,14 @@
 //   * the accumulator D[128 x 64] lives in tensor memory; tcgen05.ld 32x32b hands every thread the 64
 //     exponents of ITS path, so the payoff needs no cross-thread traffic either.
 //   * K is walked in two halves of 32 normals through one 32-column A buffer, so a tile needs
-//     64 (D) + 32 (A hi) + 32 (A lo) = 128 tensor-memory columns; a CTA of 256 threads runs two tiles side by
-//     side (256 columns), two CTAs per SM use all 512.  For a triangular factor the second half only
+//     64 (D) + 32 (A hi) + 32 (A lo) = 128 tensor-memory columns; the SM's one CTA runs four tiles side by side
+//     (all 512 columns): two sub-blocks of 256 worker threads, two tiles each.  For a triangular factor the second half only
 //     reaches assets 32..63: its MMAs run with N = 32 on the upper half of D.
 //   * pipeline: the MMAs of a half (12 x UMMA 128xNx8) are issued by one thread per tile and complete
 //     asynchronously (tcgen05.commit -> mbarrier) while all threads generate the next normals: the second half's
 //     while the first half multiplies, and the first three Philox blocks of the NEXT round while the second half
-//     multiplies (the payoff of a round is collected after them).  The hand-off "A buffer written" is a named
-//     barrier on which only the issuing warp waits; the other three warps of the tile arrive and go on.
+//     multiplies (the payoff of a round is collected after them).  The hand-off "A buffer written" is a shared-memory
+//     counter: the warp of the tile that arrives last issues the MMAs, the other three go on.
 //
 // The chunk structure, the per-thread accumulation order and the exact-integer combine are those of
 // mc_accumulate_kernel (device_common.cuh): price and half-width stay bit-identical for any grid
@@ -64,7 +64,8 @@ constexpr uint32_t kTcSbo = 128;                   // between 8-row groups
 struct BasketTcShared {
     __align__(128) float b_hi[kTcWidth * kTcWidth];
     __align__(128) float b_lo[kTcWidth * kTcWidth];
-    __align__(8) unsigned long long mbar[2];  // one per tile (128 threads)
+    __align__(8) unsigned long long mbar[4];  // one per tile (128 threads)
+    unsigned int arrivals[4][2];              // per (tile, K half): warps that have written their A columns, ever
     uint32_t tmem_base;
 };
 
@@ -116,23 +117,19 @@ __device__ __forceinline__ void wait_phase(uint32_t bar, uint32_t parity, bool &
 }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// "A buffer written" hand-off of one tile (128 worker threads) to the CTA's issuing warp: a named barrier per
-// (tile, K half) on which the workers only ARRIVE (and go on drawing normals) and the issuing warp waits.
-// Two arrivals of a worker on the same barrier are always separated by a wait on the completion of the MMAs that
-// the first one released, so phases cannot mix.
-constexpr int kTcHandoffThreads = 128 + 32;
-template <int kHalf>
-__device__ __forceinline__ void tile_arrive(int tile)
+// "A buffer written" hand-off inside a tile (4 warps): every warp counts itself in with an acquire-release
+// shared-memory atomic once its A columns are written; the warp that arrives LAST -- the one the tile would have
+// waited for anyway -- enqueues the tile's MMAs, the other three go straight on drawing normals.  The counter only
+// grows (4 per hand-off), so nothing has to be reset between rounds.  No extra warp: 16 warps per SM, 4 per
+// scheduler, leave the full 128 registers per thread, and this kernel lives on instruction-level parallelism
+// (with a dedicated 17th issuing warp one scheduler holds 5 warps and ptxas is capped at 96 registers).
+__device__ __forceinline__ bool tile_arrive_is_last(unsigned int *counter)
 {
-    if (tile == 0)
-        asm volatile("bar.arrive %0, %1;" ::"n"(1 + kHalf), "n"(kTcHandoffThreads) : "memory");
-    else
-        asm volatile("bar.arrive %0, %1;" ::"n"(3 + kHalf), "n"(kTcHandoffThreads) : "memory");
-}
-template <int kHalf, int kTile>
-__device__ __forceinline__ void tile_await()
-{
-    asm volatile("bar.sync %0, %1;" ::"n"(1 + 2 * kTile + kHalf), "n"(kTcHandoffThreads) : "memory");
+    unsigned int old = 0;
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(counter)) : "memory");
+    old = __shfl_sync(0xffffffffu, old, 0);
+    return (old & 3u) == 3u;
 }
 
 // 16 consecutive columns of this thread's tensor-memory lane
@@ -184,7 +181,8 @@ struct BasketTcTile {
     uint32_t tile_d;   // same, lane field 0 (MMA operand)
     uint32_t bar;      // shared-memory address of the tile's mbarrier
     uint32_t b_hi, b_lo;
-    int tile;          // 0 / 1 inside the CTA
+    int tile;          // 0 .. 3 inside the CTA
+    unsigned int *arrivals;  // this tile's two hand-off counters
     bool dead;         // a tensor-core wait timed out
 };
 
@@ -205,23 +203,27 @@ __device__ __forceinline__ BasketTcTile basket_tc_setup(BasketTcShared &sh)
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          (uint32_t)__cvta_generic_to_shared(&sh.tmem_base)),
-                     "n"(256)
+                     "n"(512)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (tid < 8)
+        (&sh.arrivals[0][0])[tid] = 0u;
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&sh.mbar[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&sh.mbar[1])) : "memory");
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&sh.mbar[i])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
     BasketTcTile t;
-    t.tile = (tid >> 7) & 1;  // (the issuing warp, tid >= 256, never uses its view)
+    t.tile = (tid >> 7) & 3;  // sub-block * 2 + half of the sub-block
     t.tile_d = sh.tmem_base + (uint32_t)t.tile * 128u;
     t.lane_d = t.tile_d + ((uint32_t)((warp & 3) * 32) << 16);
     t.bar = (uint32_t)__cvta_generic_to_shared(&sh.mbar[t.tile]);
+    t.arrivals = &sh.arrivals[t.tile][0];
     t.b_hi = (uint32_t)__cvta_generic_to_shared(sh.b_hi);
     t.b_lo = (uint32_t)__cvta_generic_to_shared(sh.b_lo);
     t.dead = false;
@@ -233,7 +235,7 @@ __device__ __forceinline__ void basket_tc_teardown(BasketTcShared &sh)
     tc::fence_before();
     __syncthreads();
     if ((threadIdx.x >> 5) == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "n"(512) : "memory");
 }
 
 // 16 normals -> exact hi / lo split -> 16 columns of the A_hi and A_lo buffers of this thread's lane
@@ -307,45 +309,29 @@ struct BasketTcHalf {
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc::fence_before();
-        tc::tile_arrive<kHalf>(t.tile);
+        if (tc::tile_arrive_is_last(t.arrivals + kHalf)) {
+            // the tile's A buffer is complete: one lane enqueues the 12 MMAs (3xTF32 over four K steps of 8) + commit
+            if ((threadIdx.x & 31) == 0) {
+                tc::fence_after();
+                constexpr bool kUpper = kHalf == 1 && !kFull;     // a triangular factor: normals 32..63 only reach assets 32..63
+                constexpr uint32_t n0 = kUpper ? 32 : 0;
+                constexpr uint32_t idesc = tc::instr_desc(kUpper ? 32 : 64);
+                constexpr uint32_t brow = (n0 / 8) * 128;          // byte offset of row n0 inside a K chunk
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {                   // one MMA covers K = 8 tf32 = two 16-byte chunks
+                    const uint32_t koff = brow + (uint32_t)(kHalf * 4 + ks) * 2u * kTcLbo;
+                    const uint64_t bh = tc::smem_desc(t.b_hi + koff), bl = tc::smem_desc(t.b_lo + koff);
+                    const uint32_t ah = t.tile_d + 64 + ks * 8, al = t.tile_d + 96 + ks * 8;
+                    tc::mma_ts(t.tile_d + n0, ah, bh, idesc, (kHalf > 0 || ks > 0) ? 1u : 0u);
+                    tc::mma_ts(t.tile_d + n0, al, bh, idesc, 1u);
+                    tc::mma_ts(t.tile_d + n0, ah, bl, idesc, 1u);
+                }
+                tc::commit(t.bar);
+            }
+            __syncwarp();
+        }
     }
 };
-
-// The issuing warp's side of a hand-off: wait until the 128 workers of tile kTile have written the A buffer of K
-// half kHalf, then one lane enqueues the tile's 12 MMAs (3xTF32 over four K steps of 8) and their commit.
-template <int kHalf, int kTile, bool kFull>
-__device__ __forceinline__ void basket_tc_issue(uint32_t tmem_base, uint32_t b_hi, uint32_t b_lo, uint32_t bar0)
-{
-    tc::tile_await<kHalf, kTile>();
-    if ((threadIdx.x & 31) == 0) {
-        tc::fence_after();
-        constexpr bool kUpper = kHalf == 1 && !kFull;     // a triangular factor: normals 32..63 only reach assets 32..63
-        constexpr uint32_t n0 = kUpper ? 32 : 0;
-        constexpr uint32_t idesc = tc::instr_desc(kUpper ? 32 : 64);
-        constexpr uint32_t brow = (n0 / 8) * 128;          // byte offset of row n0 inside a K chunk
-        const uint32_t tile_d = tmem_base + kTile * 128;
-#pragma unroll
-        for (int ks = 0; ks < 4; ks++) {                   // one MMA covers K = 8 tf32 = two 16-byte chunks
-            const uint32_t koff = brow + (uint32_t)(kHalf * 4 + ks) * 2u * kTcLbo;
-            const uint64_t bh = tc::smem_desc(b_hi + koff), bl = tc::smem_desc(b_lo + koff);
-            const uint32_t ah = tile_d + 64 + ks * 8, al = tile_d + 96 + ks * 8;
-            tc::mma_ts(tile_d + n0, ah, bh, idesc, (kHalf > 0 || ks > 0) ? 1u : 0u);
-            tc::mma_ts(tile_d + n0, al, bh, idesc, 1u);
-            tc::mma_ts(tile_d + n0, ah, bl, idesc, 1u);
-        }
-        tc::commit(bar0 + kTile * 8);
-    }
-    __syncwarp();
-}
-// one round of both tiles
-template <bool kFull>
-__device__ __forceinline__ void basket_tc_issue_round(uint32_t tmem_base, uint32_t b_hi, uint32_t b_lo, uint32_t bar0)
-{
-    basket_tc_issue<0, 0, kFull>(tmem_base, b_hi, b_lo, bar0);
-    basket_tc_issue<0, 1, kFull>(tmem_base, b_hi, b_lo, bar0);
-    basket_tc_issue<1, 0, kFull>(tmem_base, b_hi, b_lo, bar0);
-    basket_tc_issue<1, 1, kFull>(tmem_base, b_hi, b_lo, bar0);
-}
 
 template <int... kI>
 __device__ __forceinline__ void basket_tc_payoff_half(const unsigned long long (&d)[16], unsigned long long &sum2,
@@ -409,92 +395,84 @@ struct BasketTcParams {
     PhiloxKeys keys;
 };
 
-// mc_accumulate_kernel with the tile machinery around it.  A CTA is 8 worker warps (the 256 threads of the chunk
-// geometry: every one runs every round, paths beyond the job's total are computed and not counted) plus one
-// issuing warp that does nothing but turn hand-offs into MMAs, so the tensor-core bookkeeping (~12 instructions
-// per UMMA: descriptors, uniform-register moves, election) is off the workers' critical path.  With the issue
-// code on a worker warp the other three warps of its tile waited for it a quarter of the time
-// (profiles/r01i_basket64_f32_tensor_worker_issue.txt).
-constexpr int kTcThreads = kThreads + 32;
+// mc_accumulate_kernel with the tile machinery around it.  ONE CTA per SM: two sub-blocks of 256 threads (each
+// the "block" of the stream definition with its own chunk walk and scratch; every thread runs every round, paths
+// beyond the job's total are computed and not counted), i.e. four tiles on the SM's 512 tensor-memory columns and
+// exactly 16 warps, which leaves 128 registers per thread.  History of the MMA issue code (~12 instructions per UMMA:
+// descriptors, uniform-register moves, election): on a fixed worker warp the other three warps of its tile waited
+// for it a quarter of the time (profiles/r01i_basket64_f32_tensor_worker_issue.txt); on a dedicated 17th warp the
+// register cap fell to 96 and the latency-bound worker code lost its instruction-level parallelism (at 138
+// registers ONE CTA of 288 threads per SM was only 14 % slower than two at 96, profiles/r01i_tc_experiments.txt);
+// now the last warp to arrive at a hand-off issues.
+constexpr int kTcSubBlocks = 2;
+constexpr int kTcThreads = kTcSubBlocks * kThreads;
 
 template <bool kFull>
-__global__ void __launch_bounds__(kTcThreads, 2)
+__global__ void __launch_bounds__(kTcThreads, 1)
 basket_tc_accumulate_kernel(const __grid_constant__ BasketTcParams P, const __grid_constant__ Geometry G,
                             unsigned long long *__restrict__ acc)
 {
-    __shared__ BlockScratch sc;
+    __shared__ BlockScratch scs[kTcSubBlocks];
     __shared__ BasketTcShared sh;
-    scratch_init(sc);
-    BasketTcTile t = basket_tc_setup(sh);
+    const int sub = (int)(threadIdx.x / kThreads), tid = (int)(threadIdx.x % kThreads);
+    BlockScratch &sc = scs[sub];
+    if (tid < kAccWords)
+        sc.acc[tid] = 0ull;
+    BasketTcTile t = basket_tc_setup(sh);  // ends with a CTA-wide barrier
     const unsigned long long last = G.first_chunk + G.n_chunks;
-    if (threadIdx.x >= kThreads) {
-        // ---- issuing warp ----
-        const uint32_t tmem_base = sh.tmem_base, bar0 = (uint32_t)__cvta_generic_to_shared(&sh.mbar[0]);
-        for (unsigned long long chunk = G.first_chunk + blockIdx.x; chunk < last; chunk += gridDim.x) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * kTcSubBlocks;
+    for (unsigned long long chunk = G.first_chunk + (unsigned long long)blockIdx.x * kTcSubBlocks + sub; chunk < last; chunk += stride) {
+        const unsigned long long base = chunk * G.chunk_units;
+        const bool whole = base + G.chunk_units <= G.total_paths;
+        const unsigned long long n_valid = whole ? G.chunk_units : (G.total_paths > base ? G.total_paths - base : 0ull);
+        float s = 0, s2 = 0;
+        const uint32_t lo0 = (uint32_t)base + tid, hi = (uint32_t)(base >> 32);
+        const float no_carry[4] = {0.f, 0.f, 0.f, 0.f};
+        float W0[BasketTcHalf<0>::kWindow];
+        BasketTcHalf<0>::first(P.keys, lo0, hi, W0, no_carry);
 #pragma unroll 1
-            for (int k = 0; k < G.rounds; k++)
-                basket_tc_issue_round<kFull>(tmem_base, t.b_hi, t.b_lo, bar0);
-            __syncthreads();  // the two barriers of chunk_commit
-            __syncthreads();
-        }
-    } else {
-        // ---- workers ----
-        for (unsigned long long chunk = G.first_chunk + blockIdx.x; chunk < last; chunk += gridDim.x) {
-            const unsigned long long base = chunk * G.chunk_units;
-            const bool whole = base + G.chunk_units <= G.total_paths;
-            const unsigned long long n_valid = whole ? G.chunk_units : (G.total_paths > base ? G.total_paths - base : 0ull);
-            float s = 0, s2 = 0;
-            const uint32_t lo0 = (uint32_t)base + threadIdx.x, hi = (uint32_t)(base >> 32);
-            const float no_carry[4] = {0.f, 0.f, 0.f, 0.f};
-            float W0[BasketTcHalf<0>::kWindow];
-            BasketTcHalf<0>::first(P.keys, lo0, hi, W0, no_carry);
-#pragma unroll 1
-            for (int k = 0; k < G.rounds; k++) {
-                const unsigned long long unit = base + (unsigned long long)k * kThreads + threadIdx.x;
-                basket_tc_enqueue<kFull>(P.keys, lo0 + (uint32_t)(k * kThreads), hi, W0, t);
-                // software pipeline: the next round's first draws run while this round's last MMAs complete
-                if (k + 1 < G.rounds)
-                    BasketTcHalf<0>::first(P.keys, lo0 + (uint32_t)((k + 1) * kThreads), hi, W0, no_carry);
-                const float v = basket_tc_collect(t);
-                if (whole || unit < G.total_paths) {
-                    s += v;
-                    s2 = fmaf(v, v, s2);
-                }
+        for (int k = 0; k < G.rounds; k++) {
+            const unsigned long long unit = base + (unsigned long long)k * kThreads + tid;
+            basket_tc_enqueue<kFull>(P.keys, lo0 + (uint32_t)(k * kThreads), hi, W0, t);
+            // software pipeline: the next round's first draws run while this round's last MMAs complete
+            if (k + 1 < G.rounds)
+                BasketTcHalf<0>::first(P.keys, lo0 + (uint32_t)((k + 1) * kThreads), hi, W0, no_carry);
+            const float v = basket_tc_collect(t);
+            if (whole || unit < G.total_paths) {
+                s += v;
+                s2 = fmaf(v, v, s2);
             }
-            chunk_commit((double)s, (double)s2, n_valid, G, sc);
         }
-        if (t.dead && (threadIdx.x & 127) == 0)
-            atomicAdd(&sc.acc[11], 1ull);
+        chunk_commit<kTcSubBlocks>((double)s, (double)s2, n_valid, G, sc, sub, tid);
     }
+    if (t.dead && (tid & 127) == 0)
+        atomicAdd(&sc.acc[11], 1ull);
     __syncthreads();
-    finish(sc, acc, G);
+    finish(sc, acc, G, tid);
     basket_tc_teardown(sh);
 }
 
 // Per-path values of units [first_unit, first_unit + n_units) through the same tile machinery.
 template <bool kFull>
-__global__ void __launch_bounds__(kTcThreads, 2)
+__global__ void __launch_bounds__(kTcThreads, 1)
 basket_tc_paths_kernel(const __grid_constant__ BasketTcParams P, unsigned long long first_unit, unsigned long long n_units,
                        float *__restrict__ out)
 {
     __shared__ BasketTcShared sh;
+    const int sub = (int)(threadIdx.x / kThreads), tid = (int)(threadIdx.x % kThreads);
     BasketTcTile t = basket_tc_setup(sh);
-    if (threadIdx.x >= kThreads) {
-        const uint32_t tmem_base = sh.tmem_base, bar0 = (uint32_t)__cvta_generic_to_shared(&sh.mbar[0]);
-        for (unsigned long long blk = blockIdx.x; blk * kThreads < n_units; blk += gridDim.x)
-            basket_tc_issue_round<kFull>(tmem_base, t.b_hi, t.b_lo, bar0);
-    } else {
-        for (unsigned long long blk = blockIdx.x; blk * kThreads < n_units; blk += gridDim.x) {
-            const unsigned long long i = blk * kThreads + threadIdx.x;
-            const unsigned long long unit = first_unit + i;
-            const float no_carry[4] = {0.f, 0.f, 0.f, 0.f};
-            float W0[BasketTcHalf<0>::kWindow];
-            BasketTcHalf<0>::first(P.keys, (uint32_t)unit, (uint32_t)(unit >> 32), W0, no_carry);
-            basket_tc_enqueue<kFull>(P.keys, (uint32_t)unit, (uint32_t)(unit >> 32), W0, t);
-            const float v = basket_tc_collect(t);
-            if (i < n_units)
-                out[i] = t.dead ? __int_as_float(0x7fc00000) : v;
-        }
+    const unsigned long long n_blocks = (n_units + kThreads - 1) / kThreads;
+    const unsigned long long stride = (unsigned long long)gridDim.x * kTcSubBlocks;
+    for (unsigned long long blk = (unsigned long long)blockIdx.x * kTcSubBlocks + sub; blk < n_blocks; blk += stride) {
+        const unsigned long long i = blk * kThreads + tid;
+        const unsigned long long unit = first_unit + i;
+        const float no_carry[4] = {0.f, 0.f, 0.f, 0.f};
+        float W0[BasketTcHalf<0>::kWindow];
+        BasketTcHalf<0>::first(P.keys, (uint32_t)unit, (uint32_t)(unit >> 32), W0, no_carry);
+        basket_tc_enqueue<kFull>(P.keys, (uint32_t)unit, (uint32_t)(unit >> 32), W0, t);
+        const float v = basket_tc_collect(t);
+        if (i < n_units)
+            out[i] = t.dead ? __int_as_float(0x7fc00000) : v;
     }
     basket_tc_teardown(sh);
 }

@@ -465,7 +465,7 @@ static cudaError_t launch_tc(const BasketJob &job, const Geometry *geom, int gri
         basket_tc_accumulate_kernel<kFull><<<grid, kTcThreads, 0, stream>>>(p, *geom, d_acc);
     } else {
         const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
-        basket_tc_paths_kernel<kFull><<<(int)(blocks < 296ull ? blocks : 296ull), kTcThreads, 0, stream>>>(p, first_unit, n_units,
+        basket_tc_paths_kernel<kFull><<<(int)((blocks + 1) / 2 < 148ull ? (blocks + 1) / 2 : 148ull), kTcThreads, 0, stream>>>(p, first_unit, n_units,
                                                                                                        (float *)d_out);
     }
     return cudaGetLastError();
@@ -519,7 +519,7 @@ int basket_padded_width(int n)
 int basket_blocks_per_sm(int precision, int n, bool full)
 {
     if (basket_uses_tensor_cores(precision, n))
-        return 2;  // 2 CTAs x 256 tensor-memory columns = all 512
+        return 1;  // one CTA per SM: four tiles = all 512 tensor-memory columns
 
 #define MCB_OCC(R, W, F) occupancy_t<R, W, F>()
     MCB_BASKET_DISPATCH(MCB_OCC)

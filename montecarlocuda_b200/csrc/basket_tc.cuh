@@ -291,8 +291,8 @@ struct BasketTcHalf {
         for (int lb = 0; lb < kBlocksFirst16; lb++)
             draw(keys, path_lo, path_hi, lb, W);
     }
-    // stage 2: store columns 0..15, draw the rest, store columns 16..31, hand the A buffer to the issuing warp,
-    // which enqueues the tile's 12 MMAs.  The A buffer must be free when this is called.
+    // stage 2: store columns 0..15, draw the rest, store columns 16..31, count this warp in; the last warp of the tile
+    // to do so enqueues the tile's 12 MMAs.  The A buffer must be free when this is called.
     template <bool kFull>
     static __device__ __forceinline__ void rest(const PhiloxKeys &keys, uint32_t path_lo, uint32_t path_hi, float *W,
                                                 float (&carry)[4], BasketTcTile &t)

@@ -316,7 +316,6 @@ int make_cva_job(int precision, const mcb200_cva_t *c, uint64_t seed, CvaTables 
             d.sig = 0;
             d.kd = o.k;
         }
-        d.rkd = 1.0 / d.kd;
     }
     if (!(std::fabs(std::log(o.s / o.k)) + n * (std::fabs((o.r - 0.5 * o.v * o.v) * dt) + 9.0 * o.v * std::sqrt(dt)) < 700.0))
         return MCB200_ERR_INVALID;  // range of the table-driven exponential

@@ -6,8 +6,10 @@
 //   y  += mu_dt + sig_dt z                      exact GBM step
 //   s   = K e^y
 //   d1  = y inv_j + c1_j,  d2 = d1 - sig_j      inv_j = 1/(v sqrt(tau_j)), c1_j = (r + v^2/2) tau_j inv_j
-//   phi(d2) = phi(d1) s / kd_j                  kd_j = K e^{-r tau_j}: no second exponential
-//   ee  = s cnd(d1) - kd_j cnd(d2)              Hastings cnd, like the reference
+//   A   = s phi(d1) = K/sqrt(2 pi) e^{y - d1^2/2}  one exponential; kd_j phi(d2) = A as well (kd_j = K e^{-r tau_j})
+//   q_i = cnd-tail(|d_i|) / phi(d_i)             Hastings polynomial in 1 / (1 + 0.2316419 |d_i|), like the reference
+//   ee  = s cnd(d1) - kd_j cnd(d2)
+//       = s [d1 > 0] - kd_j [d2 > 0] - A (sgn(d1) q1 - sgn(d2) q2)
 //   cva += w_j ee                               w_j = LGD (e^{-lambda t_{j-1}} - e^{-lambda t_j})
 // so a path-step costs one normal, two exponentials and two reciprocals; the reference spends six
 // exponentials, a log, three square roots and four divisions on it.  Dates the reference drops
@@ -23,17 +25,17 @@ namespace mcb {
 
 template <typename Real>
 struct CvaDate {
-    Real w, inv, c1, sig, kd, rkd;
+    Real w, inv, c1, sig, kd;
 };
 
 constexpr int kCvaMaxDates = 1024;
 __constant__ __align__(16) unsigned char c_cva_table[kCvaMaxDates * sizeof(CvaDate<double>)];
 static TableLock g_cva_lock;
 
-// pdf * polynomial(k), k = 1 / (1 + 0.2316419 |d|): the upper-tail probability of |d|
+// q(d) = cnd-tail(|d|) / phi(d) = k polynomial(k), k = 1 / (1 + 0.2316419 |d|)
 // (Abramowitz-Stegun 26.2.17, the constants of DP/MonteCarloKernel.cu:111-116)
 template <typename Real, bool kBank = false>
-__device__ __forceinline__ Real hastings_tail(Real d, Real pdf)
+__device__ __forceinline__ Real hastings_ratio(Real d)
 {
     if constexpr (kBank) {
         const MathConsts64 &K = kMathConsts64;  // constant-bank operands instead of re-materialised immediates
@@ -42,33 +44,47 @@ __device__ __forceinline__ Real hastings_tail(Real d, Real pdf)
         poly = fma(k, poly, K.hast_a3);
         poly = fma(k, poly, K.hast_a2);
         poly = fma(k, poly, K.hast_a1);
-        return pdf * (k * poly);
+        return k * poly;
     } else {
         const Real k = rcp_real(fma((Real)0.2316419, fabs(d), (Real)1.0));
         Real poly = fma(k, (Real)1.330274429, (Real)-1.821255978);
         poly = fma(k, poly, (Real)1.781477937);
         poly = fma(k, poly, (Real)-0.356563782);
         poly = fma(k, poly, (Real)0.31938153);
-        return pdf * (k * poly);
+        return k * poly;
     }
 }
 
-// max(a, -700) for a <= 0 without touching the fp64 pipe: negative doubles order like their high
-// words taken as unsigned integers, so one integer min on the high word does it (-inf included).
+// sgn(d) q for q > 0 and x [d > 0], by the sign bit of d on the integer pipe (the fp64 comparisons are
+// DSETPs on the pipe that binds).  d = +0 counts as positive where the reference's `d > 0` does not:
+// cnd(0) is 1/2 from either branch.
+__device__ __forceinline__ double with_sign_of(double q, double d)
+{
+    return __hiloint2double(__double2hiint(q) ^ (__double2hiint(d) & (int)0x80000000), __double2loint(q));
+}
+__device__ __forceinline__ float with_sign_of(float q, float d)
+{
+    return __int_as_float(__float_as_int(q) ^ (__float_as_int(d) & (int)0x80000000));
+}
+__device__ __forceinline__ double keep_if_positive(double x, double d)
+{
+    const int keep = ~(__double2hiint(d) >> 31);
+    return __hiloint2double(__double2hiint(x) & keep, __double2loint(x) & keep);
+}
+__device__ __forceinline__ float keep_if_positive(float x, float d)
+{
+    return __int_as_float(__float_as_int(x) & ~(__float_as_int(d) >> 31));
+}
+
+// max(a, -700) without touching the fp64 pipe: negative doubles order like their high words taken as
+// unsigned integers and every non-negative one lies below them, so one integer min on the high word does
+// it (-inf included).
 __device__ __forceinline__ double floor_at_minus_700(double a)
 {
     const unsigned hi = min((unsigned)__double2hiint(a), 0xC085E000u);  // high word of -700.0
     return __hiloint2double((int)hi, hi == 0xC085E000u ? 0 : __double2loint(a));
 }
 __device__ __forceinline__ float floor_at_minus_700(float a) { return a; }  // MUFU.EX2(-inf) = 0
-
-template <typename Real, bool kBank = false> __device__ __forceinline__ Real inv_sqrt_2pi()
-{
-    if constexpr (kBank)
-        return kMathConsts64.inv_sqrt_2pi;
-    else
-        return (Real)0.39894228040143267793994605993438;
-}
 
 template <typename RealT, bool kAccumLayout = false>
 struct Cva {
@@ -80,7 +96,7 @@ struct Cva {
     static constexpr int kNpb = NormalsPerBlock<RealT>::value;
     struct Params {
         PhiloxKeys keys;
-        Real y0, mu_dt, k;
+        Real y0, mu_dt, k, k_pdf;  // k_pdf = K / sqrt(2 pi)
         PolarScale<Real> scale;  // of sig_dt = v sqrt(dt), folded under the Box-Muller square root
         int n_dates;  // kept dates
     };
@@ -95,15 +111,12 @@ struct Cva {
         const Real s = P.k * exp_real(y, sh);
         const Real d1 = fma(y, D.inv, D.c1);
         const Real d2 = d1 - D.sig;
-        // -d1^2/2 can be -1e14 (a date a few ulps before maturity) or -inf (exact grid, tau = 0):
-        // floor it where e^x is already 0 for every purpose, so the table-driven exp stays in range
-        const Real pdf1 = inv_sqrt_2pi<Real, kBank>() * exp_real(floor_at_minus_700((Real)-0.5 * d1 * d1), sh);
-        const Real pdf2 = pdf1 * s * D.rkd;
-        const Real t1 = hastings_tail<Real, kBank>(d1, pdf1);
-        const Real t2 = hastings_tail<Real, kBank>(d2, pdf2);
-        const Real n1 = d1 > 0 ? (Real)1.0 - t1 : t1;
-        const Real n2 = d2 > 0 ? (Real)1.0 - t2 : t2;
-        const Real ee = s * n1 - D.kd * n2;
+        // s phi(d1) = kd phi(d2) = K / sqrt(2 pi) e^{y - d1^2/2}.  The exponent can be -1e14 (a date a few ulps before
+        // maturity) or -inf (exact grid, tau = 0): floor it where e^x is already 0 for every purpose, so the
+        // table-driven exp stays in range
+        const Real a = P.k_pdf * exp_real(floor_at_minus_700(fma((Real)-0.5 * d1, d1, y)), sh);
+        const Real tails = with_sign_of(hastings_ratio<Real, kBank>(d1), d1) - with_sign_of(hastings_ratio<Real, kBank>(d2), d2);
+        const Real ee = fma(-a, tails, keep_if_positive(s, d1) - keep_if_positive(D.kd, d2));
         cva = fma(D.w, ee, cva);
     }
     static __device__ __forceinline__ void eval(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
@@ -138,6 +151,7 @@ static typename W::Params narrow(const CvaJob &job)
     p.mu_dt = (Real)job.mu_dt;
     p.scale = polar_scale<Real>(job.sig_dt);
     p.k = (Real)job.k;
+    p.k_pdf = (Real)(job.k * 0.39894228040143267793994605993438);
     p.n_dates = job.n_dates;
     return p;
 }
@@ -152,7 +166,7 @@ static cudaError_t launch_t(const CvaJob &job, const Geometry *geom, int grid, u
     std::vector<CvaDate<Real>> staging((size_t)(job.n_dates > 0 ? job.n_dates : 1));
     for (int j = 0; j < job.n_dates; j++) {
         const CvaDateHost &h = job.dates[j];
-        staging[j] = CvaDate<Real>{(Real)h.w, (Real)h.inv, (Real)h.c1, (Real)h.sig, (Real)h.kd, (Real)h.rkd};
+        staging[j] = CvaDate<Real>{(Real)h.w, (Real)h.inv, (Real)h.c1, (Real)h.sig, (Real)h.kd};
     }
     TableUse use(g_cva_lock, stream, staging.data(), staging.size() * sizeof(CvaDate<Real>));
     if (use.status() != cudaSuccess)

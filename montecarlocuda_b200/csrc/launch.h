@@ -45,7 +45,7 @@ cudaError_t basket_paths(int precision, const BasketJob &job, unsigned long long
 
 // ---- CVA (DP/MonteCarloKernel.cu:104-129, :222-283) ----
 struct CvaDateHost {
-    double w, inv, c1, sig, kd, rkd;
+    double w, inv, c1, sig, kd;
 };
 struct CvaJob {
     PhiloxKeys keys;

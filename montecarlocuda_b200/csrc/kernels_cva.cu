@@ -24,8 +24,8 @@
 namespace mcb {
 
 template <typename Real>
-struct CvaDate {
-    Real w, inv, c1, sig, kd;
+struct alignas(16) CvaDate {  // three 16-byte constant loads per date
+    Real w, inv, c1, sig, kd, pad;
 };
 
 constexpr int kCvaMaxDates = 1024;
@@ -124,15 +124,27 @@ struct Cva {
     {
         const CvaDate<Real> *dates = reinterpret_cast<const CvaDate<Real> *>(c_cva_table);
         Real y = P.y0, cva = 0;
+        // whole draw blocks run their kNpb dates back to back with no test in between: only y links one date to the
+        // next, so the exponentials and reciprocals of neighbouring dates overlap
+        const int n_whole = P.n_dates / kNpb;
 #pragma unroll 1
-        for (int jb = 0; jb * kNpb < P.n_dates; jb++) {
+        for (int jb = 0; jb < n_whole; jb++) {
             uint32_t w[4];
             philox4x32_10(path_lo, path_hi, (uint32_t)jb, kTagCva, P.keys, w);
             Real sr[kNpb / 2], cs[kNpb / 2], sn[kNpb / 2];
             polar_from_words<true>(w, sr, cs, sn, sh, P.scale);
 #pragma unroll
-            for (int q = 0; q < kNpb; q++) {
-                const int j = jb * kNpb + q;
+            for (int q = 0; q < kNpb; q++)
+                step(P, dates[jb * kNpb + q], sr[q / 2], (q & 1) ? sn[q / 2] : cs[q / 2], y, cva, sh);
+        }
+        if (n_whole * kNpb < P.n_dates) {
+            uint32_t w[4];
+            philox4x32_10(path_lo, path_hi, (uint32_t)n_whole, kTagCva, P.keys, w);
+            Real sr[kNpb / 2], cs[kNpb / 2], sn[kNpb / 2];
+            polar_from_words<true>(w, sr, cs, sn, sh, P.scale);
+#pragma unroll
+            for (int q = 0; q < kNpb - 1; q++) {
+                const int j = n_whole * kNpb + q;
                 if (j < P.n_dates)
                     step(P, dates[j], sr[q / 2], (q & 1) ? sn[q / 2] : cs[q / 2], y, cva, sh);
             }
@@ -166,7 +178,7 @@ static cudaError_t launch_t(const CvaJob &job, const Geometry *geom, int grid, u
     std::vector<CvaDate<Real>> staging((size_t)(job.n_dates > 0 ? job.n_dates : 1));
     for (int j = 0; j < job.n_dates; j++) {
         const CvaDateHost &h = job.dates[j];
-        staging[j] = CvaDate<Real>{(Real)h.w, (Real)h.inv, (Real)h.c1, (Real)h.sig, (Real)h.kd};
+        staging[j] = CvaDate<Real>{(Real)h.w, (Real)h.inv, (Real)h.c1, (Real)h.sig, (Real)h.kd, (Real)0};
     }
     TableUse use(g_cva_lock, stream, staging.data(), staging.size() * sizeof(CvaDate<Real>));
     if (use.status() != cudaSuccess)

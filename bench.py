@@ -46,16 +46,59 @@ WORKLOADS = {
     "cva50_f64_2p26": dict(kind="cva", dates=50, prec="f64", paths=1 << 26, bound="fp64", work=133.0, units_per_path=50),
     "basket64_f32_2p30": dict(kind="basket", n=64, prec="f32", paths=1 << 30, bound="issue", work=3236.0, units_per_path=1),
 }
-PIPE_PER_CLK_PER_SM = {"fp64": 64.0, "mufu": 16.0, "issue": 128.0}
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the workload's kernel at the full path count, from the
-# `ncu --set full` captures summarised under profiles/ (bytes, source file): the path has no HBM-resident data
-DRAM_TRAFFIC = {
-    "vanilla_f64_2p32": (69_120, "profiles/r01n_vanilla_f64_2p32.txt"),
-    "vanilla_f32_2p32": (17_920, "profiles/r01n_vanilla_f32_2p32.txt"),
-    "basket10_f64_2p28": (118_528, "profiles/r01n_basket10_f64_2p28.txt"),
-    "cva50_f64_2p26": (87_296, "profiles/r01n_cva50_f64_2p26.txt"),
-    "basket64_f32_2p30": (124_160, "profiles/r01n_basket64_f32_2p30_tensor.txt"),
+# the other precision of each config (the reference ships every workload in both): `--also everything`; their
+# per-unit work is derived here by the same rule as SURVEY.md 8(d) (not SURVEY figures)
+EXTRA_WORKLOADS = {
+    "basket10_f32_2p28": dict(kind="basket", n=10, prec="f32", paths=1 << 28, bound="mufu", work=30.0, units_per_path=1,
+                              work_note="10 x (lg2, sqrt, sin, cos)/2 + 10 ex2"),
+    "cva50_f32_2p26": dict(kind="cva", dates=50, prec="f32", paths=1 << 26, bound="mufu", work=8.0, units_per_path=50,
+                           work_note="per path-step: normal 2, spot ex2, pdf ex2, 2 x cnd (rcp + ex2 shared -> 2 rcp), 2 spare"),
+    "basket64_f64_2p30": dict(kind="basket", n=64, prec="f64", paths=1 << 30, bound="fp64", work=5476.0, units_per_path=1,
+                              work_note="64 x 34 normal + 2080 triangular FMA + 64 x 18 exp + 64 + 4"),
 }
+WORKLOADS.update(EXTRA_WORKLOADS)
+PIPE_PER_CLK_PER_SM = {"fp64": 64.0, "mufu": 16.0, "issue": 128.0}
+# `ncu --set full` capture of ONE launch of the workload's kernel at the full path count, condensed by
+# tools/ncu_summary.py (committed under profiles/): source of roofline.traffic (dram__bytes_read.sum +
+# dram__bytes_write.sum; the path has no HBM-resident data) and of roofline.pipe_active (what the counters say)
+NCU_SUMMARY = {
+    "vanilla_f64_2p32": "profiles/r01p_vanilla_f64_2p32.txt",
+    "vanilla_f32_2p32": "profiles/r01p_vanilla_f32_2p32.txt",
+    "basket10_f64_2p28": "profiles/r01p_basket10_f64_2p28.txt",
+    "cva50_f64_2p26": "profiles/r01p_cva50_f64_2p26.txt",
+    "basket64_f32_2p30": "profiles/r01p_basket64_f32_2p30_tensor.txt",
+}
+_BYTE_UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+_PIPE_METRICS = {
+    "fp64": "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "xu_mufu": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "fma": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "alu": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "tensor": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "issue_slots": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "shared_memory": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+}
+
+
+def ncu_summary(name):
+    """{metric: (value, unit)} of the committed ncu summary of a workload's kernel, or {}."""
+    path = NCU_SUMMARY.get(name)
+    out = {}
+    if not path:
+        return out
+    try:
+        for line in (ROOT / path).read_text().splitlines():
+            parts = line.split()
+            if len(parts) >= 2 and ("__" in parts[0]):
+                try:
+                    out[parts[0]] = (float(parts[1].replace(",", "")), parts[2] if len(parts) > 2 else "")
+                except ValueError:
+                    pass
+    except OSError:
+        pass
+    return out
+
+
 HEADLINE = "vanilla_f64_2p32"
 
 
@@ -324,8 +367,20 @@ def roofline(w, value, clocks, name=None):
     f_run = (clocks or {}).get("sm_mhz")
     if f_run:
         out["frac_at_sampled_clock"] = achieved / (pipe * SM_COUNT * f_run * 1e6)
-    if name in DRAM_TRAFFIC:
-        out["traffic"], out["traffic_source"] = DRAM_TRAFFIC[name][0], DRAM_TRAFFIC[name][1] + " (bytes per launch, 1 GPU, whole job)"
+    summary = ncu_summary(name)
+    if summary:
+        rd, wr = summary.get("dram__bytes_read.sum"), summary.get("dram__bytes_write.sum")
+        if rd and wr:
+            out["traffic"] = rd[0] * _BYTE_UNITS.get(rd[1], 1.0) + wr[0] * _BYTE_UNITS.get(wr[1], 1.0)
+            out["traffic_source"] = NCU_SUMMARY[name] + " (bytes per launch, 1 GPU, whole job)"
+        # the hardware's own answer next to the canonical-work fraction: busiest pipes of that capture (fractions of
+        # their peak while the kernel ran); frac > 1 only says the kernel needs fewer instructions than the canon
+        active = {k: round(summary[m][0] / 100.0, 4) for k, m in _PIPE_METRICS.items() if m in summary and summary[m][0] >= 1.0}
+        if active:
+            out["pipe_active"] = dict(sorted(active.items(), key=lambda kv: -kv[1]))
+            out["pipe_active_source"] = NCU_SUMMARY[name] + " (ncu --set full, one launch at the full path count)"
+    if "work_note" in w:
+        out["work_source"] = "derived by the rule of SURVEY.md 8(d): " + w["work_note"]
     return out
 
 
@@ -336,7 +391,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
-    ap.add_argument("--also", default="all", help="'all', 'none' or a comma list of extra workloads reported under 'also'")
+    ap.add_argument("--also", default="all", help="'all' (the BASELINE configs), 'everything' (+ the other precision of each), 'none' or a comma list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--combine", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: cross-GPU sum inside the pricing kernel over peer memory (peer) or one NCCL all-reduce after it")
@@ -366,7 +421,8 @@ def main():
 
     main_run = time_workload(args.workload, w, pricer, dist, torch, rank, world, args.steps, args.warmup, sample_clocks=(rank == 0), gpu_index=local)
     also = {}
-    extra = [] if args.also == "none" else ([k for k in WORKLOADS if k != args.workload] if args.also == "all" else args.also.split(","))
+    extra = [] if args.also == "none" else ([k for k in WORKLOADS if k != args.workload and (args.also == "everything" or k not in EXTRA_WORKLOADS)]
+                                                if args.also in ("all", "everything") else args.also.split(","))
     for name in extra:
         ww = WORKLOADS[name]
         r = time_workload(name, ww, pricer, dist, torch, rank, world, max(2, args.steps // 2), 3, sample_clocks=(rank == 0), gpu_index=local)

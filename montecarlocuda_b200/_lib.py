@@ -3,6 +3,7 @@ loudly: there is no Python, NumPy or CPU implementation of the pricing path behi
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 LIB_DIR = Path(__file__).resolve().parent / "lib"
@@ -103,7 +104,9 @@ _lib = None
 
 
 def library_path() -> Path:
-    return LIB_DIR / "libmcb200.so"
+    # MCB200_LIBRARY: an explicitly named build of the same library (A/B timing of kernel variants)
+    override = os.environ.get("MCB200_LIBRARY")
+    return Path(override) if override else LIB_DIR / "libmcb200.so"
 
 
 def load() -> C.CDLL:

@@ -9,7 +9,7 @@
 //                                         fdlibm kernel polynomials on [0, pi/4]                     18 fp64
 //   exp_tab        e^x                    n = rint(256 x / ln2) by magic add, Cody-Waite, table of
 //                                         2^(j/256), degree-4 expm1, exponent added as an integer     9 fp64
-//   rcp_newton     1/x                    MUFU.RCP64H seed + 2 Newton steps                           4 fp64
+//   rcp_newton     1/x                    MUFU.RCP64H seed + 1 cubic step                             3 fp64
 //
 // Accuracy (checked on the CPU against libm by tests/test_device_math64.py through the host build
 // of this very header, and on the GPU against the oracle): <= 2 ulp for exp/sqrt/rcp/sincos,
@@ -131,6 +131,11 @@ struct Tables64 {
 // per bank group: thread t reads replica t % 8 (16-byte entries: 128 bytes per index, one bank group per replica)
 // or t % 16 (8-byte entries), so threads that are served together can never share a bank.  Same values, same
 // arithmetic, bit-identical results; 64 KB instead of 6 KB, shared by all warps of a (large) CTA.
+// The two angle tables (16 KB each) stay single copies: 2.6 wavefronts per quarter-warp instead of 1 (22 of the 29
+// wavefronts of a Box-Muller pair).  Four copies each (thread t reads replica t % 4: 1.9 wavefronts per quarter-warp,
+// 192 KB in all) were measured and are SLOWER -- European call 10.15 vs 9.73 ms, basket-10 7.26 vs 7.21 ms
+// (profiles/r01p_ab_experiments.txt): once log and exp were conflict-free the shared-memory pipe stopped being what
+// binds, and the wider index arithmetic costs more than the wavefronts give back.
 struct Tables64Rep {
     static constexpr bool kConstBank = false;
     double log_rep[256][8][2];    // [index][replica]{ c_i, -ln c_i }
@@ -244,13 +249,13 @@ template <bool kShort = false> MCB_FN double sqrt_pos(double x)
 }
 
 // ---- 1/x, x finite and not tiny ------------------------------------------------------------------
+// One cubically convergent step from the 2^-22 seed: with e = 1 - x y, 1/x = y (1 + e + e^2 + ...), and
+// y (1 + e + e^2) is off by e^3 < 2^-60 -- three fp64 instructions where two Newton steps take four.
 MCB_FN double rcp_newton(double x)
 {
-    double y = rcp_seed(x);
-    double e = fma_(-x, y, 1.0);
-    y = fma_(y, e, y);
-    e = fma_(-x, y, 1.0);
-    return fma_(y, e, y);
+    const double y = rcp_seed(x);
+    const double e = fma_(-x, y, 1.0);
+    return fma_(y, fma_(e, e, e), y);
 }
 
 // ---- cos and sin of 2 pi k / 2^52 for a 52-bit integer k = (k_hi[19:0] : k_lo) --------------------
@@ -309,6 +314,8 @@ template <class Tab> MCB_FN double exp_tab(double x, const Tab &T)
     p = fma_(r, p, 0.5);
     p = fma_(r * r, p, r);          // e^r - 1
     const double v = fma_(tj, p, tj);
+    // (the exponent insertion as mask + IMAD -- one instruction fewer than shift, mask, add -- was measured: European
+    // call 2 % slower, basket-10 1.3 % faster, CVA 1 % slower, profiles/r01p_ab_experiments.txt; not used)
     return make_double(hi_word(v) + ((n >> 8) << 20), lo_word(v));
 }
 

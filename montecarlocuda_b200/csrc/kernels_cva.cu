@@ -21,6 +21,15 @@
 #include "launch.h"
 #include "table_lock.h"
 
+#ifndef MCB_CVA_SUBBLOCKS
+// sub-blocks of 256 threads around one table set.  2: 128 registers per thread, 17.41 ms; 3: 80 registers, 17.89 ms
+// (profiles/r01p_ab_experiments.txt; tools/build_variant.sh builds the other one for A/B timing)
+#define MCB_CVA_SUBBLOCKS 2
+#endif
+#ifndef MCB_CVA_BANK
+#define MCB_CVA_BANK 0  // fp64 math constants as constant-bank operands (1) or literals (0): at 128 registers literals win, 16.92 vs 17.01 ms
+#endif
+
 namespace mcb {
 
 template <typename Real>
@@ -91,7 +100,7 @@ struct Cva {
     using Real = RealT;
     static constexpr int kUnitPaths = 1;
     static constexpr int kUnroll = 1;
-    static constexpr int kSubBlocks = (kAccumLayout && sizeof(RealT) == 8) ? 3 : 1;  // fp64: one table set per SM
+    static constexpr int kSubBlocks = (kAccumLayout && sizeof(RealT) == 8) ? MCB_CVA_SUBBLOCKS : 1;  // fp64: one table set per SM
     static constexpr int kMinBlocks = kSubBlocks > 1 ? 1 : 3;
     static constexpr int kNpb = NormalsPerBlock<RealT>::value;
     struct Params {
@@ -101,8 +110,9 @@ struct Cva {
         int n_dates;  // kept dates
     };
     // fp64 pricing kernel: replicated tables + constant-bank math constants (80-register cap, see device_math64.cuh)
-    static constexpr bool kBank = kAccumLayout && sizeof(RealT) == 8;
-    using Shared = std::conditional_t<kBank, SharedTables64RepBank, typename SharedFor<Real>::type>;
+    static constexpr bool kBank = kAccumLayout && sizeof(RealT) == 8 && MCB_CVA_BANK;
+    using Shared = std::conditional_t<kBank, SharedTables64RepBank,
+                                      std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>>;
     // one exposure date; the diffusion sig_dt z arrives as (sig_dt r) * (cos or sin) and folds into the step's FMA
     static __device__ __forceinline__ void step(const Params &P, const CvaDate<Real> &D, Real sr, Real trig, Real &y,
                                                 Real &cva, const Shared &sh)

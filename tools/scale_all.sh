@@ -12,9 +12,11 @@ run() { # n combine tag extra...
   tail -c 300 gpurun_out/scale_$tag.err | tail -2
 }
 run 8 peer 8
+if [ -z "$QUICK" ]; then  # QUICK=1: only the 8-GPU and the 1-GPU run (8x box time is charged)
 run 8 nccl 8_nccl
 run 4 peer 4
 run 2 peer 2
+fi
 run 1 peer 1
 timeout 900 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/pytest_multi8.log 2>&1; tail -3 gpurun_out/pytest_multi8.log
 python - <<'PY'

@@ -152,6 +152,13 @@ struct SharedFactor64 : SharedTables64Rep {
             factor[i] = src[i];
     }
 };
+// Wide fp64 baskets (two-pass sweep, see Basket::eval_two_pass): the plain math tables plus one slot per thread and
+// sub-block for each normal of the first half ([normal][thread]: consecutive threads, conflict-free 8-byte accesses).
+// 38 KB + 2 x 64 KB; the replicated tables (96 KB) would not fit next to the slots.
+template <int kHalf>
+struct SharedTwoPass64 : SharedTables64 {
+    double stash[2][kHalf][kThreads];
+};
 // xa, xb += {2 consecutive factor entries at smem address base + kByteOffset} * z
 template <int kByteOffset>
 __device__ __forceinline__ void fma_pair_shared_f64(double &xa, double &xb, double z, uint32_t base)
@@ -197,7 +204,13 @@ struct Basket {
     static constexpr int kUnitPaths = 1;
     static constexpr int kUnroll = 1;
     // fp64: the CTAs of 256 threads an SM holds become ONE CTA of that many sub-blocks around one (replicated) table set
-    static constexpr int kSubBlocks = (kAccumLayout && sizeof(RealT) == 8) ? basket_min_blocks(N, 8) : 1;
+    // fp64, 64 assets: 64 accumulators + generator need 255 registers, i.e. 8 warps per SM, and the kernel sat at 27 % of
+    // the fp64 pipe (758 ms for 2^30 paths, profiles/r01p_bench_all_precisions.json).  Two passes of 32 accumulators
+    // (assets 0..31, then 32..63 with the first 32 normals parked in shared memory) fit 128 registers: twice the warps,
+    // the same FMAs in the same order per accumulator and the same summation order -- bit-identical values.
+    static constexpr bool kTwoPass = kAccumLayout && sizeof(RealT) == 8 && N == 64 && !kFull;
+    static constexpr int kHalf = N / 2;
+    static constexpr int kSubBlocks = kTwoPass ? 2 : (kAccumLayout && sizeof(RealT) == 8) ? basket_min_blocks(N, 8) : 1;
     static constexpr int kMinBlocks = kSubBlocks > 1 ? 1 : basket_min_blocks(N, (int)sizeof(Real));
     static constexpr int kNpb = NormalsPerBlock<RealT>::value;
     struct Params {
@@ -207,9 +220,11 @@ struct Basket {
     // fp64 pricing kernels from 8 assets up read the factor from shared memory too (see SharedFactor64)
     static constexpr bool kSharedFactor64 = kAccumLayout && sizeof(RealT) == 8 && N >= 8 && N <= 16;  // wider: ptxas spills more than it saves
     using Shared = std::conditional_t<
+        kTwoPass, SharedTwoPass64<kHalf>,
+        std::conditional_t<
         kSharedFactor, SharedFactor<(kSharedFactor ? Table::kFactor : 1)>,
         std::conditional_t<kSharedFactor64, SharedFactor64<(kSharedFactor64 ? Table::kFactor : 1)>,
-                           std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>>>;
+                           std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>>>>;
     template <class Sh> static __device__ __forceinline__ Real grow(Real x, const Sh &sh)
     {
         if constexpr (sizeof(Real) == 4)
@@ -333,9 +348,91 @@ struct Basket {
         ((sum = fma(table_entry<Real, kMBase + kI * (int)sizeof(Real)>(), grow(exponent<kI>(st), sh), sum)), ...);
         return positive_part(sum);
     }
+    // ---- two-pass sweep (kTwoPass) ----
+    // rows kRow0 + kRow... of column J into the accumulators x[row - kOff]
+    template <int J, int kRow0, int kOff, int... kRow>
+    static __device__ __forceinline__ void column_rows(Real (&x)[kHalf], Real z, std::integer_sequence<int, kRow...>)
+    {
+        ((x[kRow0 + kRow - kOff] =
+              fma(table_entry<Real, kFactorBase + Table::index(J, kRow0 + kRow) * (int)sizeof(Real)>(), z, x[kRow0 + kRow - kOff])),
+         ...);
+    }
+    // draw block JB of the first half: normals 4 JB .. 4 JB + 3 -> their slots and the rows J .. kHalf-1
+    template <int JB, int... kQ>
+    static __device__ __forceinline__ void first_half_block(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&x)[kHalf],
+                                                            const Shared &sh, Real (*slots)[kThreads], std::integer_sequence<int, kQ...>)
+    {
+        uint32_t w[4];
+        philox4x32_10(path_lo, path_hi, (uint32_t)JB, kTagBasket, P.keys, w);
+        Real z[kNpb];
+        normals_from_words(w, z, sh);
+        ((slots[JB * kNpb + kQ][0] = z[kQ]), ...);
+        (column_rows<JB * kNpb + kQ, JB * kNpb + kQ, 0>(x, z[kQ], std::make_integer_sequence<int, kHalf - (JB * kNpb + kQ)>{}), ...);
+    }
+    // draw block JB of the second half: rows J .. N-1 (all in the upper half)
+    template <int JB, int... kQ>
+    static __device__ __forceinline__ void second_half_block(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&x)[kHalf],
+                                                             const Shared &sh, std::integer_sequence<int, kQ...>)
+    {
+        uint32_t w[4];
+        philox4x32_10(path_lo, path_hi, (uint32_t)JB, kTagBasket, P.keys, w);
+        Real z[kNpb];
+        normals_from_words(w, z, sh);
+        (column_rows<JB * kNpb + kQ, JB * kNpb + kQ, kHalf>(x, z[kQ], std::make_integer_sequence<int, N - (JB * kNpb + kQ)>{}), ...);
+    }
+    template <int... kJB>
+    static __device__ __forceinline__ void first_half(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&x)[kHalf],
+                                                      const Shared &sh, Real (*slots)[kThreads], std::integer_sequence<int, kJB...>)
+    {
+        (first_half_block<kJB>(P, path_lo, path_hi, x, sh, slots, std::make_integer_sequence<int, kNpb>{}), ...);
+    }
+    template <int... kJB>
+    static __device__ __forceinline__ void second_half(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&x)[kHalf],
+                                                       const Shared &sh, std::integer_sequence<int, kJB...>)
+    {
+        (second_half_block<kHalf / kNpb + kJB>(P, path_lo, path_hi, x, sh, std::make_integer_sequence<int, kNpb>{}), ...);
+    }
+    // the dense block: parked normal J times rows kHalf .. N-1
+    template <int... kJ>
+    static __device__ __forceinline__ void parked_columns(Real (&x)[kHalf], Real (*slots)[kThreads], std::integer_sequence<int, kJ...>)
+    {
+        (column_rows<kJ, kHalf, kHalf>(x, slots[kJ][0], std::make_integer_sequence<int, kHalf>{}), ...);
+    }
+    template <int kFirst, int... kI>
+    static __device__ __forceinline__ void half_init(Real (&x)[kHalf], std::integer_sequence<int, kI...>)
+    {
+        ((x[kI] = table_entry<Real, kABase + (kFirst + kI) * (int)sizeof(Real)>()), ...);
+    }
+    template <int kFirst, int... kI>
+    static __device__ __forceinline__ Real half_value(const Real (&x)[kHalf], Real sum, const Shared &sh, std::integer_sequence<int, kI...>)
+    {
+        ((sum = fma(table_entry<Real, kMBase + (kFirst + kI) * (int)sizeof(Real)>(), grow(x[kI], sh), sum)), ...);
+        return sum;
+    }
+    static __device__ __forceinline__ void eval_two_pass(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
+                                                         const Shared &sh)
+    {
+        static_assert(!kTwoPass || (kHalf % kNpb == 0 && N % kNpb == 0), "halves must fall on draw-block boundaries");
+        // this thread's column of slots: [normal][thread]
+        Real (*slots)[kThreads] =
+            reinterpret_cast<Real (*)[kThreads]>(const_cast<Real *>(&sh.stash[threadIdx.x / kThreads][0][threadIdx.x % kThreads]));
+        using Half = std::make_integer_sequence<int, kHalf>;
+        Real x[kHalf];
+        half_init<0>(x, Half{});
+        first_half(P, path_lo, path_hi, x, sh, slots, std::make_integer_sequence<int, kHalf / kNpb>{});
+        Real sum = half_value<0>(x, -table_entry<Real, kKBase>(), sh, Half{});
+        half_init<kHalf>(x, Half{});
+        parked_columns(x, slots, Half{});
+        second_half(P, path_lo, path_hi, x, sh, std::make_integer_sequence<int, (N - kHalf) / kNpb>{});
+        v[0] = positive_part(half_value<kHalf>(x, sum, sh, Half{}));
+    }
     static __device__ __forceinline__ void eval(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
                                                 const Shared &sh)
     {
+        if constexpr (kTwoPass) {
+            eval_two_pass(P, path_lo, path_hi, v, sh);
+            return;
+        }
         State st;
         init(st, std::make_integer_sequence<int, (kPaired ? N / 2 : N)>{});
         sweep(P, path_lo, path_hi, st, sh, std::make_integer_sequence<int, kBlocks>{});

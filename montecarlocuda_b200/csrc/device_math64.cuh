@@ -47,7 +47,9 @@ namespace hostmath {
 // LDC 6 per step).  From the constant bank they are plain DFMA operands (CVA 20.4 -> 19.8 ms).  Kernels with
 // registers to spare keep the literals: there ptxas holds them in registers across the loop and the constant-bank
 // operands are slower (vanilla fp64 9.72 -> 10.36 ms when forced), so the choice rides on the table type
-// (Tab::kConstBank) the kernel instantiates the functions with.
+// (Tab::kConstBank) the kernel instantiates the functions with.  Since the CVA kernel runs 2 sub-blocks of 256 threads
+// (128 registers) it keeps the literals too (16.92 vs 17.01 ms); the constant-bank route stays selectable
+// (MCB_CVA_BANK=1 together with MCB_CVA_SUBBLOCKS=3, kernels_cva.cu).
 struct MathConsts64 {
     double log_magic;          // 2^52 + 1023
     double log_c6, log_c5, log_c3;   // -1/6, 1/5, 1/3   (-1/4, -1/2 are immediates)

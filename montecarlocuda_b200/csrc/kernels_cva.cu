@@ -109,7 +109,8 @@ struct Cva {
         PolarScale<Real> scale;  // of sig_dt = v sqrt(dt), folded under the Box-Muller square root
         int n_dates;  // kept dates
     };
-    // fp64 pricing kernel: replicated tables + constant-bank math constants (80-register cap, see device_math64.cuh)
+    // fp64 pricing kernel: replicated tables; math constants from the constant bank only when asked (MCB_CVA_BANK: the
+    // right choice under the 80-register cap of 3 sub-blocks, see device_math64.cuh)
     static constexpr bool kBank = kAccumLayout && sizeof(RealT) == 8 && MCB_CVA_BANK;
     using Shared = std::conditional_t<kBank, SharedTables64RepBank,
                                       std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>>;

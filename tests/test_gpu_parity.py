@@ -262,8 +262,8 @@ def test_accumulator_matches_oracle_restatement(engine, oracle):
                                                     ("basket", 10, "f32"), ("basket", 64, "f64"), ("cva", 0, "f64"), ("cva", 0, "f32")])
 def test_pricing_kernels_sum_exactly_their_path_kernels_values(engine, oracle, workload, n_assets, prec):
     """The pricing kernels run a different memory layout from the per-path kernels the oracle is compared with
-    (bank-conflict-free replicated fp64 tables, sub-block CTAs, the fp64 factor in shared memory, math constants from
-    the constant bank) but the SAME arithmetic: the accumulator of a job equals, bit for bit, the oracle's restatement
+    (bank-conflict-free replicated fp64 tables, sub-block CTAs, the fp64 factor in shared memory, the two-pass sweep of
+    the 64-asset fp64 basket, whole draw blocks of CVA dates) but the SAME arithmetic: the accumulator of a job equals, bit for bit, the oracle's restatement
     of the chunk reduction applied to the per-path kernel's values."""
     params = make_basket(oracle, n_assets, prec) if workload == "basket" else CVA50
     n = 40_000 if n_assets < 64 else 9_000

@@ -157,7 +157,7 @@ struct SharedFactor64 : SharedTables64Rep {
 // 38 KB + 2 x 64 KB; the replicated tables (96 KB) would not fit next to the slots.
 template <int kHalf>
 struct SharedTwoPass64 : SharedTables64 {
-    double stash[2][kHalf][kThreads];
+    double stash[2][kHalf][kThreads];  // [sub-block]: Basket::kSubBlocks == 2 for the two-pass kernel (static_assert there)
 };
 // xa, xb += {2 consecutive factor entries at smem address base + kByteOffset} * z
 template <int kByteOffset>
@@ -413,6 +413,7 @@ struct Basket {
                                                          const Shared &sh)
     {
         static_assert(!kTwoPass || (kHalf % kNpb == 0 && N % kNpb == 0), "halves must fall on draw-block boundaries");
+        static_assert(!kTwoPass || kSubBlocks == 2, "SharedTwoPass64 holds the slots of two sub-blocks");
         // this thread's column of slots: [normal][thread]
         Real (*slots)[kThreads] =
             reinterpret_cast<Real (*)[kThreads]>(const_cast<Real *>(&sh.stash[threadIdx.x / kThreads][0][threadIdx.x % kThreads]));

@@ -121,7 +121,7 @@ def test_basket_full_matrix_factor(engine, oracle):
 
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-@pytest.mark.parametrize("n_dates", [25, 50, 75])
+@pytest.mark.parametrize("n_dates", [1, 2, 3, 7, 25, 50, 75])   # whole draw blocks, tails of every length, no block at all
 def test_cva_paths_match_oracle(engine, oracle, prec, n_dates):
     cva = m.CVA(0.03, 0.6, m.OptionData(100.0, 100.0, 0.05, 0.2, 1.0), n_dates)
     n, first, seed = 2048, 512, 31337
@@ -259,13 +259,16 @@ def test_accumulator_matches_oracle_restatement(engine, oracle):
 
 
 @pytest.mark.parametrize("workload,n_assets,prec", [("basket", 10, "f64"), ("basket", 16, "f64"), ("basket", 8, "f64"), ("basket", 3, "f64"),
-                                                    ("basket", 10, "f32"), ("basket", 64, "f64"), ("cva", 0, "f64"), ("cva", 0, "f32")])
+                                                    ("basket", 10, "f32"), ("basket", 64, "f64"), ("basket", 40, "f64"), ("cva", 0, "f64"), ("cva", 0, "f32"), ("cva", 7, "f64"), ("cva", 3, "f32"),
+                                                    ("cva", 2, "f64")])
 def test_pricing_kernels_sum_exactly_their_path_kernels_values(engine, oracle, workload, n_assets, prec):
     """The pricing kernels run a different memory layout from the per-path kernels the oracle is compared with
     (bank-conflict-free replicated fp64 tables, sub-block CTAs, the fp64 factor in shared memory, the two-pass sweep of
     the 64-asset fp64 basket, whole draw blocks of CVA dates) but the SAME arithmetic: the accumulator of a job equals, bit for bit, the oracle's restatement
     of the chunk reduction applied to the per-path kernel's values."""
-    params = make_basket(oracle, n_assets, prec) if workload == "basket" else CVA50
+    # for the CVA the second parameter is the number of exposure dates (0: the 50 of BASELINE config 4)
+    params = (make_basket(oracle, n_assets, prec) if workload == "basket" else
+              CVA50 if n_assets == 0 else m.CVA(0.03, 0.6, m.OptionData(100.0, 100.0, 0.05, 0.2, 1.0), n_assets))
     n = 40_000 if n_assets < 64 else 9_000
     p, acc = _shard_accumulators(engine, workload, params, n, prec, 5, 1)
     vals = getattr(engine, workload + "_paths")(params, 0, n, prec, 5)

@@ -164,11 +164,17 @@ __device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float
 // The first version spent a whole block per pair (52-bit radius and angle): twice the IMAD.WIDE
 // work for bits no estimate can see.  All arithmetic after the bits is fp64: 12 (log) + 7 (sqrt) +
 // 4 (cos/sin from the two-level table) + 2 = 25 fp64 instructions per pair (libdevice: 68+).
+// No |.| around the logarithm: u = 2 - f is a multiple of 2^-44, so k ln u is either the tiny positive offset (u == 1)
+// or at least 2^-43 |k| / 2 -- four orders of magnitude above the function's rounding error (checked on the host over
+// every u = 1 - j 2^-44, j <= 2e6: min 1.1366e-13, error 2.7e-17).  With a 52-bit radius it could come out as -1e-17,
+// and the fabs cost an fp64 instruction per pair (MUFU.RSQ64H cannot take an operand modifier).  Bit-identical
+// values; basket-10 7.20 -> 7.12 ms, CVA 16.93 -> 16.61 ms.  The European call is the exception: 0.3 % FASTER with the
+// extra instruction (9.711 vs 9.740 ms, profiles/r01p_ab_experiments.txt), so polar_from_words keeps it there.
 template <class Tab>
 __device__ __forceinline__ void box_muller_f64(uint32_t wa, uint32_t wb, double &z0, double &z1, const Tab &T)
 {
     const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
-    const double r = sqrt_pos<true>(fabs(neg2log_unit(2.0 - f, T)));
+    const double r = sqrt_pos<true>(neg2log_unit(2.0 - f, T));
     double cs, sn;
     sincos_turn20(wb & 0x000fffffu, cs, sn, T);
     z0 = r * cs;
@@ -225,7 +231,8 @@ __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], double 
     for (int i = 0; i < 2; i++) {
         const uint32_t wa = w[2 * i], wb = w[2 * i + 1];
         const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
-        br[i] = sqrt_pos<kShortSqrt>(fabs(scaled_log_unit(2.0 - f, sh.t, S.c, S.c_ln2)));
+        const double r2 = scaled_log_unit(2.0 - f, sh.t, S.c, S.c_ln2);
+        br[i] = sqrt_pos<kShortSqrt>(kShortSqrt ? r2 : fabs(r2));  // kShortSqrt == false: the European call (see box_muller_f64)
         sincos_turn20(wb & 0x000fffffu, cs[i], sn[i], sh.t);
     }
 }

@@ -64,7 +64,7 @@ PIPE_PER_CLK_PER_SM = {"fp64": 64.0, "mufu": 16.0, "issue": 128.0}
 NCU_SUMMARY = {
     "vanilla_f64_2p32": "profiles/r01p_vanilla_f64_2p32.txt",
     "vanilla_f32_2p32": "profiles/r01p_vanilla_f32_2p32.txt",
-    "basket10_f64_2p28": "profiles/r01p_basket10_f64_2p28.txt",
+    "basket10_f64_2p28": "profiles/r01q_basket10_f64_2p28.txt",
     "cva50_f64_2p26": "profiles/r01q_cva50_f64_2p26.txt",
     "basket64_f32_2p30": "profiles/r01p_basket64_f32_2p30_tensor.txt",
 }

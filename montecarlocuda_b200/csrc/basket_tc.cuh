@@ -132,6 +132,15 @@ __device__ __forceinline__ bool tile_arrive_is_last(unsigned int *counter)
     return (old & 3u) == 3u;
 }
 
+// one lane of a converged warp, chosen by the hardware (elect.sync): unlike `lane == 0` the compiler knows the
+// branch holds exactly one thread, so a UMMA inside it is issued straight from uniform registers
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t picked;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(picked));
+    return picked != 0;
+}
+
 // 16 consecutive columns of this thread's tensor-memory lane
 __device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&v)[16])
 {
@@ -219,8 +228,10 @@ __device__ __forceinline__ BasketTcTile basket_tc_setup(BasketTcShared &sh)
     __syncthreads();
     tc::fence_after();
     BasketTcTile t;
-    t.tile = (tid >> 7) & 3;  // sub-block * 2 + half of the sub-block
-    t.tile_d = sh.tmem_base + (uint32_t)t.tile * 128u;
+    // warp-uniform by construction, and said so to the compiler (a shuffle from lane 0): the MMA issue code then takes
+    // its tensor-memory addresses from uniform registers instead of an ELECT / R2UR.BROADCAST loop around every UMMA
+    t.tile = __shfl_sync(0xffffffffu, (tid >> 7) & 3, 0);  // sub-block * 2 + half of the sub-block
+    t.tile_d = __shfl_sync(0xffffffffu, sh.tmem_base + (uint32_t)t.tile * 128u, 0);
     t.lane_d = t.tile_d + ((uint32_t)((warp & 3) * 32) << 16);
     t.bar = (uint32_t)__cvta_generic_to_shared(&sh.mbar[t.tile]);
     t.arrivals = &sh.arrivals[t.tile][0];
@@ -311,7 +322,7 @@ struct BasketTcHalf {
         tc::fence_before();
         if (tc::tile_arrive_is_last(t.arrivals + kHalf)) {
             // the tile's A buffer is complete: one lane enqueues the 12 MMAs (3xTF32 over four K steps of 8) + commit
-            if ((threadIdx.x & 31) == 0) {
+            if (tc::elect_one()) {
                 tc::fence_after();
                 constexpr bool kUpper = kHalf == 1 && !kFull;     // a triangular factor: normals 32..63 only reach assets 32..63
                 constexpr uint32_t n0 = kUpper ? 32 : 0;

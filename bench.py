@@ -66,7 +66,7 @@ NCU_SUMMARY = {
     "vanilla_f32_2p32": "profiles/r01p_vanilla_f32_2p32.txt",
     "basket10_f64_2p28": "profiles/r01q_basket10_f64_2p28.txt",
     "cva50_f64_2p26": "profiles/r01q_cva50_f64_2p26.txt",
-    "basket64_f32_2p30": "profiles/r01p_basket64_f32_2p30_tensor.txt",
+    "basket64_f32_2p30": "profiles/r01q_basket64_f32_2p30_tensor.txt",
 }
 _BYTE_UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 _PIPE_METRICS = {

@@ -35,7 +35,8 @@ enum {
     MCB200_ERR_NO_DEVICE = 3,   /* no CUDA device / device index out of range */
     MCB200_ERR_OVERFLOW = 4,    /* a partial sum left the 160-bit fixed-point window, or was NaN */
     MCB200_ERR_UNSUPPORTED = 5, /* e.g. basket wider than MCB200_MAX_ASSETS */
-    MCB200_ERR_ALIGNMENT = 6    /* shard boundary not on a chunk boundary */
+    MCB200_ERR_ALIGNMENT = 6,   /* shard boundary not on a chunk boundary */
+    MCB200_ERR_PEER_TIMEOUT = 7 /* a peer rank's partial sums did not arrive in time (fused combine), or were pulled too late */
 };
 
 enum { MCB200_F32 = 0, MCB200_F64 = 1 };
@@ -82,7 +83,7 @@ typedef struct {
     double expected;     /* reference `Expected`: e^{-rT} * mean (pricing) or mean (CVA) */
     double confidence;   /* reference `Confidence`: 1.96 * s / sqrt(n) of the UNdiscounted value */
     double std_error;    /* standard error of `expected` (discounted where expected is) */
-    double kernel_ms;    /* device time of the pricing kernel(s), CUDA events, max over devices */
+    double kernel_ms;    /* device time of the pricing kernel(s), CUDA events, max over devices; 0 unless MCB200_OPT_TIMING */
 } mcb200_result_t;
 
 /* Everything a shard launch and the final combine must agree on; a pure function of the job
@@ -108,6 +109,16 @@ const char *mcb200_strerror(int status);
 const char *mcb200_last_error(const mcb200_ctx *ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t mcb200_launch_count(const mcb200_ctx *ctx);
+/* Context options.
+ *   MCB200_OPT_TIMING   (default 0)  record CUDA events around the kernels of the blocking calls and report
+ *                                    mcb200_result_t.kernel_ms (two more stream operations per call; 0 otherwise).
+ *                                    The reference times every call (DP/MonteCarloKernel.cu:380-386, :447-453).
+ *   MCB200_OPT_OVERLAP  (default 0; environment MCB200_OVERLAP=1)  launch with programmatic dependent launch:
+ *                                    consecutive launches of a stream overlap the tail of one with the start of the
+ *                                    next (independent jobs only share read-only state). */
+enum { MCB200_OPT_TIMING = 1, MCB200_OPT_OVERLAP = 2 };
+int mcb200_set_option(mcb200_ctx *ctx, int option, int value);
+int mcb200_get_option(const mcb200_ctx *ctx, int option);
 /* Which kernel prices a wide single-precision basket (32 < n <= 64 assets):
  *   MCB200_BASKET_TENSOR (default)  the correlated draw L*g of brownianVect (DP/MonteCarloKernel.cu:74-87) runs on the
  *                                   tcgen05 tensor cores as a 3xTF32 128-path tile product (csrc/basket_tc.cuh);
@@ -189,6 +200,16 @@ int mcb200_peer_create(mcb200_ctx *ctx, int rank, int world, mcb200_peer **out,
 int mcb200_peer_connect(mcb200_peer *peer, const unsigned char *handles /* world x 64 bytes, rank-major */);
 int mcb200_peer_connect_local(mcb200_peer **group, int world);
 int mcb200_peer_attach(mcb200_ctx *ctx, mcb200_peer *peer /* NULL detaches */);
+/* Split phase.  MCB200_PEER_WAIT (default): as above, the kernel is the collective.  MCB200_PEER_PUSH: the last CTA only
+ * pushes the device's limbs into the mailboxes and the kernel ends -- no rank waits for the slowest one, back-to-back
+ * jobs do not lock-step; d_acc of the launch is not written.  mcb200_peer_pull then enqueues one small kernel that
+ * sums the group's MOST RECENT launch out of this rank's mailbox into d_acc (12 words, overwritten).  A mailbox keeps
+ * the last 8 launches; a pull that comes later than that, or a peer that does not answer within the timeout
+ * (default 10 s, environment MCB200_PEER_TIMEOUT_MS), ends in MCB200_ERR_PEER_TIMEOUT from mcb200_finalize. */
+enum { MCB200_PEER_WAIT = 0, MCB200_PEER_PUSH = 1 };
+int mcb200_peer_set_mode(mcb200_peer *peer, int mode);
+int mcb200_peer_set_timeout_ms(mcb200_peer *peer, double ms);
+int mcb200_peer_pull(mcb200_peer *peer, uint64_t *d_acc, void *stream);
 int mcb200_peer_destroy(mcb200_peer *peer);
 
 int mcb200_finalize(const mcb200_plan_t *plan, const uint64_t acc[MCB200_ACC_WORDS],

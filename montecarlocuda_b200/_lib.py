@@ -8,7 +8,9 @@ from pathlib import Path
 
 LIB_DIR = Path(__file__).resolve().parent / "lib"
 
-OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_OVERFLOW, ERR_UNSUPPORTED, ERR_ALIGNMENT = range(7)
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_OVERFLOW, ERR_UNSUPPORTED, ERR_ALIGNMENT, ERR_PEER_TIMEOUT = range(8)
+OPT_TIMING, OPT_OVERLAP = 1, 2
+PEER_WAIT, PEER_PUSH = 0, 1
 F32, F64 = 0, 1
 VANILLA, BASKET, CVA = 1, 2, 3
 ACC_WORDS = 12
@@ -74,6 +76,11 @@ _SIGNATURES = {
     "mcb200_peer_connect_local": (C.c_int, [_P(C.c_void_p), C.c_int]),
     "mcb200_peer_attach": (C.c_int, [_CTX, C.c_void_p]),
     "mcb200_peer_destroy": (C.c_int, [C.c_void_p]),
+    "mcb200_peer_set_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "mcb200_peer_set_timeout_ms": (C.c_int, [C.c_void_p, C.c_double]),
+    "mcb200_peer_pull": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcb200_set_option": (C.c_int, [_CTX, C.c_int, C.c_int]),
+    "mcb200_get_option": (C.c_int, [_CTX, C.c_int]),
     "mcb200_set_basket_engine": (C.c_int, [C.c_int]),
     "mcb200_get_basket_engine": (C.c_int, []),
     "mcb200_vanilla": (C.c_int, [_CTX, C.c_int, _P(OptionT), C.c_uint64, C.c_uint64, _P(ResultT)]),

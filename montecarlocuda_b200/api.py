@@ -8,7 +8,7 @@ Every number comes from libmcb200.so; nothing here computes a price.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Sequence
 
 import numpy as np
@@ -39,6 +39,9 @@ class OptionData:
     def _c(self) -> _lib.OptionT:
         return _lib.OptionT(self.s, self.k, self.r, self.v, self.t)
 
+    def _snapshot(self):
+        return (float(self.s), float(self.k), float(self.r), float(self.v), float(self.t))
+
 
 @dataclass
 class MultiOptionData:
@@ -53,7 +56,6 @@ class MultiOptionData:
     k: float
     t: float
     r: float
-    _keep: list = field(default_factory=list, repr=False, compare=False)
 
     @property
     def n(self) -> int:
@@ -64,9 +66,17 @@ class MultiOptionData:
         arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in (self.s, self.v, self.p, self.d, self.w)]
         if arrs[2].shape != (n, n) or any(a.shape != (n,) for a in (arrs[0], arrs[1], arrs[3], arrs[4])):
             raise ValueError("MultiOptionData: s, v, d, w must have n entries and p must be n x n")
-        self._keep = arrs  # keep the buffers alive while the C struct points at them
         ptr = [a.ctypes.data_as(C.POINTER(C.c_double)) for a in arrs]
-        return _lib.BasketT(n, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], self.k, self.t, self.r)
+        c = _lib.BasketT(n, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], self.k, self.t, self.r)
+        # the STRUCT owns the buffers it points at (a ctypes pointer field does not keep its array alive): every call
+        # returns an independent struct, valid for as long as the caller holds it
+        c._buffers = arrs
+        return c
+
+    def _snapshot(self):
+        """The job's parameters by value (cache keys: the dataclass is mutable)."""
+        return (tuple(np.asarray(a, dtype=np.float64).ravel().tolist() for a in (self.s, self.v, self.p, self.d, self.w)),
+                float(self.k), float(self.t), float(self.r))
 
 
 @dataclass
@@ -82,6 +92,9 @@ class CVA:
 
     def _c(self) -> _lib.CvaT:
         return _lib.CvaT(self.defInt, self.lgd, self.option._c(), int(self.n), int(self.grid_mode))
+
+    def _snapshot(self):
+        return (float(self.defInt), float(self.lgd), self.option._snapshot(), int(self.n), int(self.grid_mode))
 
 
 @dataclass
@@ -152,6 +165,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.mcb200_launch_count(self._ctx))
 
+    def set_timing(self, on: bool = True) -> None:
+        """Report OptionValue.kernel_ms (CUDA events around the kernels of the blocking calls; off by default: two
+        more stream operations per call)."""
+        _lib.check(self._lib.mcb200_set_option(self._ctx, _lib.OPT_TIMING, int(bool(on))), self._ctx)
+
+    def set_overlap(self, on: bool = True) -> None:
+        """Programmatic dependent launch: consecutive launches of a stream overlap tail and start."""
+        _lib.check(self._lib.mcb200_set_option(self._ctx, _lib.OPT_OVERLAP, int(bool(on))), self._ctx)
+
     # ---- one-call pricing (host structs in, host result out) ----
     def vanilla(self, opt: OptionData, n_paths: int, precision=F64, seed: int = DEFAULT_SEED) -> OptionValue:
         c, r = opt._c(), _lib.ResultT()
@@ -173,7 +195,7 @@ class Engine:
         with workload in {"vanilla", "basket", "cva"}.  Returns a list of OptionValue, in order."""
         jobs = list(jobs)
         codes = {"vanilla": _lib.VANILLA, "basket": _lib.BASKET, "cva": _lib.CVA}
-        c_params = [params._c() for _, params, _, _ in jobs]          # keep the C structs alive
+        c_params = [params._c() for _, params, _, _ in jobs]          # the C structs (and their buffers) live until the call returns
         arr = (_lib.JobT * len(jobs))()
         for i, (workload, _, n_paths, precision) in enumerate(jobs):
             arr[i] = _lib.JobT(codes[workload], _prec(precision), C.cast(C.pointer(c_params[i]), C.c_void_p), n_paths, seed)

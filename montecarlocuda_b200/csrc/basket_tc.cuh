@@ -425,15 +425,15 @@ basket_tc_accumulate_kernel(const __grid_constant__ BasketTcParams P, const __gr
 {
     __shared__ BlockScratch scs[kTcSubBlocks];
     __shared__ BasketTcShared sh;
+    pdl_launch_dependents();
     const int sub = (int)(threadIdx.x / kThreads), tid = (int)(threadIdx.x % kThreads);
     BlockScratch &sc = scs[sub];
     if (tid < kAccWords)
         sc.acc[tid] = 0ull;
     BasketTcTile t = basket_tc_setup(sh);  // ends with a CTA-wide barrier
-    const unsigned long long last = G.first_chunk + G.n_chunks;
-    const unsigned long long stride = (unsigned long long)gridDim.x * kTcSubBlocks;
-    for (unsigned long long chunk = G.first_chunk + (unsigned long long)blockIdx.x * kTcSubBlocks + sub; chunk < last; chunk += stride) {
-        const unsigned long long base = chunk * G.chunk_units;
+    for (ChunkWalk<kTcSubBlocks> walk(sub); walk.live(G); walk.advance(sc)) {
+        walk.claim_ahead(G, tid);
+        const unsigned long long base = (G.first_chunk + walk.chunk) * G.chunk_units;
         const bool whole = base + G.chunk_units <= G.total_paths;
         const unsigned long long n_valid = whole ? G.chunk_units : (G.total_paths > base ? G.total_paths - base : 0ull);
         float s = 0, s2 = 0;
@@ -454,7 +454,7 @@ basket_tc_accumulate_kernel(const __grid_constant__ BasketTcParams P, const __gr
                 s2 = fmaf(v, v, s2);
             }
         }
-        chunk_commit<kTcSubBlocks>((double)s, (double)s2, n_valid, G, sc, sub, tid);
+        chunk_commit<kTcSubBlocks>((double)s, (double)s2, n_valid, G, sc, sub, tid, walk.ahead);
     }
     if (t.dead && (tid & 127) == 0)
         atomicAdd(&sc.acc[11], 1ull);

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <type_traits>
+#include <utility>
 
 namespace mcb {
 
@@ -30,30 +31,68 @@ struct PhiloxKeys {
 // src's 12 accumulator words as 24 "flagged halves": every 8-byte mailbox word is {low: 32 bits of data, high: the
 // launch's flag}, written by ONE 8-byte store (atomic), so a word is valid exactly when its flag matches -- no
 // fence, no separate "ready" flag and no second NVLink round trip (the LL protocol of NCCL).
+// Two modes: kPeerWait -- the last CTA pushes, waits for its peers' halves and leaves the JOB's totals in the output
+// block (the kernel is the collective); kPeerPush -- it only pushes and ends (split phase): ranks do not lock-step on
+// the slowest one, and the totals of a launch are summed out of the mailbox when somebody asks for them
+// (peer_pull_kernel).
 constexpr int kPeerMax = 8;
-constexpr int kPeerRing = 4;
+constexpr int kPeerRing = 8;
 constexpr int kPeerHalves = 2 * kAccWords;   // 24 flagged halves per (slot, source)
 constexpr int kPeerSlotWords = 32;           // 24 used, padded to 256 bytes
 constexpr size_t kPeerMailboxBytes = (size_t)kPeerRing * kPeerMax * kPeerSlotWords * sizeof(unsigned long long);
+enum : int { kPeerWait = 0, kPeerPush = 1 };
+constexpr unsigned long long kErrPeerTimeout = 1ull << 32;   // added to accumulator word 11: a peer never answered
 struct PeerLink {
-    int world;                            // <= 1: no combine, the kernel leaves this device's partial in acc
+    int world;                            // <= 1: no combine, the kernel leaves this device's partial in the output block
     int rank;
+    int mode;                             // kPeerWait / kPeerPush
     unsigned long long seq;               // this launch's sequence number (>= 1, the same on every rank)
+    unsigned long long timeout_ns;        // bound of the wait for the peers (wall clock, %globaltimer)
     unsigned long long *mail[kPeerMax];
-    unsigned int *ticket;                 // this device's "CTAs finished" counter (zero between launches)
 };
+__host__ __device__ inline unsigned long long peer_flag(unsigned long long seq)
+{
+    // never 0 (fresh mailbox memory) and different from the flags this slot carried on its previous uses
+    return ((unsigned long long)((unsigned int)seq | 0x80000000u)) << 32;
+}
 
-// What a launch covers.  All of it derives from the JOB (total paths), never from the GPU count.
-struct Geometry {
+// Per-launch control block in device memory.  All zero between launches: the last CTA of a launch takes the totals
+// out and leaves it so (no memset in front of a launch).
+struct LaunchCtl {
+    unsigned long long acc[kAccWords];    // integer limbs added by the CTAs of this launch
+    unsigned int next;                    // chunks claimed beyond the first gridDim.x * kSubBlocks
+    unsigned int ticket;                  // CTAs that have finished
+    unsigned long long pad[3];
+};
+static_assert(sizeof(LaunchCtl) == 128, "one control block per 128 bytes");
+
+// The part of a launch that depends on the JOB only (total paths), never on the GPU count or the grid.
+struct JobGeometry {
     unsigned long long total_paths;
     unsigned long long chunk_units;   // kThreads * rounds
-    unsigned long long first_chunk;   // this shard
-    unsigned long long n_chunks;
     int rounds;                       // units per thread per chunk
     int scale_exp_sum;                // value * 2^e before the integer split
     int scale_exp_sumsq;
+    int pad;
+};
+
+// What a launch covers and where its result goes.
+struct Geometry : JobGeometry {
+    unsigned long long first_chunk;   // this shard
+    unsigned long long n_chunks;      // < 2^31 per launch (the host splits larger shards)
+    LaunchCtl *ctl;
+    // result, written by the launch's last CTA: 24 flagged halves (like a mailbox slot) into mapped pinned HOST
+    // memory, so a blocking call needs no copy and no stream synchronisation -- the host polls the flags
+    unsigned long long *host_slot;    // or nullptr
+    unsigned long long host_flag;     // peer_flag(launch number of the context)
     PeerLink peer;
 };
+
+// Programmatic dependent launch (sm_90+): the next kernel of the stream may start filling the SMs as soon as every
+// CTA of this one has started (its tail overlaps our tail), and nothing of ours is complete for it until pdl_wait().
+// Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // One Philox4x32-10 block.  The 64-bit products compile to IMAD.WIDE.U32, the mixes to LOP3.
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -101,6 +140,7 @@ struct BlockScratch {
     double s[kWarps];
     double s2[kWarps];
     unsigned long long acc[kAccWords];
+    unsigned int next;   // the chunk this sub-block runs after the current one (relative to the shard)
 };
 
 // Barrier of one sub-block: a CTA of the pricing kernel is kSubBlocks independent groups of kThreads threads
@@ -132,10 +172,12 @@ __device__ __forceinline__ void scratch_init(BlockScratch &sc, int sub = 0, int 
 // Fixed-shape reduction of one chunk: xor butterfly inside each warp (offsets 16..1, every lane
 // ends with the same value), then warps 0..7 in order on thread 0, which turns the chunk partial
 // into integer limbs held in shared memory.  The chunk partial depends only on the chunk's
-// per-path values, not on which CTA, SM or GPU ran it.
+// per-path values, not on which CTA, SM or GPU ran it.  `next` (thread 0's) is handed to the whole sub-block
+// through sc.next on the way: the chunk it runs after this one.
 template <int kSubBlocks = 1>
 __device__ __forceinline__ void chunk_commit(double s, double s2, unsigned long long n_valid,
-                                             const Geometry &G, BlockScratch &sc, int sub = 0, int tid = threadIdx.x)
+                                             const JobGeometry &G, BlockScratch &sc, int sub = 0, int tid = threadIdx.x,
+                                             unsigned int next = 0u)
 {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -160,6 +202,7 @@ __device__ __forceinline__ void chunk_commit(double s, double s2, unsigned long 
         sc.acc[10] += n_valid;
         if (!ok)
             sc.acc[11] += 1ull;
+        sc.next = next;
     }
     sub_barrier<kSubBlocks>(sub);
 }
@@ -175,14 +218,36 @@ __device__ __forceinline__ void scratch_flush(const BlockScratch &sc, unsigned l
     }
 }
 
+// Which chunk a sub-block runs next.  The first one is static (blockIdx.x * kSubBlocks + sub); the following ones are
+// claimed from the launch's counter, ONE AHEAD: thread 0 asks for the next chunk when it starts the current one and
+// only looks at the answer when the current one is committed, so the L2 round trip of the atomic never waits.
+// Legal because the combine is order-free (integer limbs): which CTA ran which chunk cannot change a bit.  Against
+// the static stride this removes the wave tail -- 10 922 chunks on 1 184 CTAs are 9.2 waves, and whoever drew ten
+// chunks kept the device waiting (profiles/r01k_scale_notes.txt).
+template <int kSubBlocks>
+struct ChunkWalk {
+    unsigned int chunk;   // relative to G.first_chunk
+    unsigned int ahead;   // thread 0 only: the claim in flight
+    __device__ __forceinline__ ChunkWalk(int sub) : chunk(blockIdx.x * kSubBlocks + sub), ahead(0u) {}
+    __device__ __forceinline__ bool live(const Geometry &G) const { return chunk < (unsigned int)G.n_chunks; }
+    __device__ __forceinline__ void claim_ahead(const Geometry &G, int tid)
+    {
+        if (tid == 0)
+            ahead = gridDim.x * kSubBlocks + atomicAdd(&G.ctl->next, 1u);
+    }
+    __device__ __forceinline__ void advance(const BlockScratch &sc) { chunk = sc.next; }
+};
+
 // ---- the collective, fused into the kernel that feeds it ----------------------------------------
 // The (sum, sum^2) combine across GPUs is 96 bytes: as a separate NCCL all-reduce it costs a kernel launch
 // and ~20-30 us of latency after a pricing kernel that, sharded over 8 GPUs, runs for 0.5-10 ms.  Here the
 // LAST CTA of each device's pricing kernel pushes the device's limbs straight into every peer's mailbox
-// (24 flagged 8-byte stores per peer over NVLink), polls its own mailbox for the peers' and adds the
-// integer limbs: when the kernel ends, acc holds the JOB's totals on every rank, bit-identical everywhere
-// (integer addition; the order of arrival cannot matter).  Slot reuse is safe with a ring of 2 or more: a rank
-// cannot finish step s + 1 before every peer has pushed step s + 1, which each peer does after reading step s.
+// (24 flagged 8-byte stores per peer over NVLink) and either ends there (kPeerPush) or polls its own mailbox
+// for the peers' and adds the integer limbs (kPeerWait): then the output block holds the JOB's totals on every
+// rank when the kernel ends, bit-identical everywhere (integer addition; the order of arrival cannot matter).
+// Slot reuse: in kPeerWait a rank cannot finish step s + 1 before every peer has pushed step s + 1, which each does
+// after reading step s; in kPeerPush nothing holds a rank back, a slot is simply overwritten kPeerRing launches
+// later, and a pull that comes too late sees a newer flag and says so instead of waiting for ever.
 __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
 {
     unsigned long long v;
@@ -193,50 +258,77 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned l
 {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
-__device__ __forceinline__ void peer_combine(unsigned long long *acc, const PeerLink &L)
+__device__ __forceinline__ unsigned long long globaltimer_ns()
 {
-    __shared__ bool s_last;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long flagged_half(const unsigned long long *words, int h, unsigned long long flag)
+{
+    const unsigned long long w = words[h >> 1];
+    return flag | ((h & 1) ? (w >> 32) : (w & 0xffffffffull));
+}
+
+// Wait (bounded, wall clock) for half h of source `src` of launch `seq` in this device's mailbox.
+// Returns 0 = arrived, 1 = timed out, 2 = overwritten by a later launch (a pull that came too late).
+__device__ __forceinline__ int peer_poll(const unsigned long long *mailbox, unsigned long long seq, int src, int h,
+                                         unsigned long long timeout_ns, unsigned int &data)
+{
+    const unsigned long long flag = peer_flag(seq);
+    const unsigned long long *p = mailbox + ((size_t)(seq % kPeerRing) * kPeerMax + src) * kPeerSlotWords + h;
+    unsigned long long t0 = 0ull;
+    for (unsigned int spin = 0;; spin++) {
+        const unsigned long long v = ld_relaxed_sys(p);
+        if ((v & 0xffffffff00000000ull) == flag) {
+            data = (unsigned int)v;
+            return 0;
+        }
+        // a flag of a LATER launch of the same slot (31-bit sequence numbers, compared modulo 2^31)
+        const unsigned int theirs = (unsigned int)(v >> 32), mine = (unsigned int)(flag >> 32);
+        if ((theirs & 0x80000000u) && ((theirs - mine) & 0x7fffffffu) != 0u && ((theirs - mine) & 0x7fffffffu) < 0x40000000u) {
+            data = 0u;
+            return 2;
+        }
+        if ((spin & 63u) == 63u) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0ull)
+                t0 = now;
+            else if (now - t0 > timeout_ns) {
+                data = 0u;
+                return 1;
+            }
+        }
+        __nanosleep(32);
+    }
+}
+
+// last CTA of a device: tot[] (shared memory, this device's 12 limbs) -> every mailbox; kPeerWait: += the peers'
+__device__ __forceinline__ void peer_exchange(unsigned long long *tot, const PeerLink &L)
+{
     __shared__ unsigned int s_late;
     __shared__ unsigned int s_half[kPeerMax * kPeerHalves];
-    __threadfence();  // this CTA's atomics on acc are ordered before its ticket
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        s_last = atomicAdd(L.ticket, 1u) == gridDim.x - 1;
-        s_late = 0u;
-    }
-    __syncthreads();
-    if (!s_last)
-        return;
-    // ---- last CTA of this device ----
-    __threadfence();
     const int tid = threadIdx.x;
     if (tid == 0)
-        *L.ticket = 0u;  // ready for the next launch on this device (stream order)
+        s_late = 0u;
+    __syncthreads();
+    const unsigned long long flag = peer_flag(L.seq);
     const size_t slot = (size_t)(L.seq % kPeerRing) * kPeerMax;
-    // never 0 (fresh mailbox memory) and different from the flag this slot carried kPeerRing launches ago
-    const unsigned long long flag = ((unsigned long long)((unsigned int)L.seq | 0x80000000u)) << 32;
     if (tid < kPeerHalves * L.world) {
         const int peer = tid / kPeerHalves, h = tid % kPeerHalves;
-        // push: half h of this device's accumulator into rank `peer`'s mailbox
-        const unsigned long long word = *((volatile unsigned long long *)acc + (h >> 1));
-        const unsigned long long half = (h & 1) ? (word >> 32) : (word & 0xffffffffull);
-        st_relaxed_sys(L.mail[peer] + (slot + L.rank) * kPeerSlotWords + h, flag | half);
-        // pull: half h of rank `peer`'s accumulator from this device's mailbox.  Bounded: a peer that never
-        // launches must end as an error flag, not as a hung device.
-        const unsigned long long *src = L.mail[L.rank] + (slot + peer) * kPeerSlotWords + h;
-        unsigned long long v = 0ull;
-        bool ok = false;
-        for (int spin = 0; spin < (1 << 22) && !ok; spin++) {
-            v = ld_relaxed_sys(src);
-            ok = (v & 0xffffffff00000000ull) == flag;
-            if (!ok)
-                __nanosleep(64);
+        // push: half h of this device's limbs into rank `peer`'s mailbox
+        st_relaxed_sys(L.mail[peer] + (slot + L.rank) * kPeerSlotWords + h, flagged_half(tot, h, flag));
+        if (L.mode == kPeerWait) {
+            // pull: half h of rank `peer`'s limbs from this device's mailbox.  Bounded: a peer that never launches
+            // must end as an error flag, not as a hung device.
+            unsigned int v;
+            if (peer_poll(L.mail[L.rank], L.seq, peer, h, L.timeout_ns, v) != 0)
+                atomicAdd(&s_late, 1u);
+            s_half[tid] = v;
         }
-        if (!ok)
-            atomicAdd(&s_late, 1u);
-        s_half[tid] = (unsigned int)v;
     }
+    if (L.mode != kPeerWait)
+        return;
     __syncthreads();
     if (tid < kAccWords) {
         unsigned long long total = 0ull;
@@ -244,17 +336,101 @@ __device__ __forceinline__ void peer_combine(unsigned long long *acc, const Peer
             total += (unsigned long long)s_half[src * kPeerHalves + 2 * tid] |
                      ((unsigned long long)s_half[src * kPeerHalves + 2 * tid + 1] << 32);
         if (tid == kAccWords - 1 && s_late)
-            total += 1ull;  // error flag: a peer did not answer
-        acc[tid] = total;
+            total += kErrPeerTimeout;
+        tot[tid] = total;
     }
+    __syncthreads();
 }
 
-// end of a pricing kernel: CTA totals -> device accumulator (-> job totals on every rank)
-__device__ __forceinline__ void finish(const BlockScratch &sc, unsigned long long *acc, const Geometry &G, int tid = threadIdx.x)
+// End of a pricing kernel: CTA totals -> the launch's control block; the LAST CTA takes the device totals out of it
+// (leaving it zeroed for the next launch), runs the cross-GPU exchange if there is one, adds the result to the
+// caller's accumulator block and/or publishes it to the host.
+__device__ __forceinline__ void finish(const BlockScratch &sc, unsigned long long *out, const Geometry &G, int tid = threadIdx.x)
 {
-    scratch_flush(sc, acc, tid);
+    __shared__ bool s_last;
+    __shared__ unsigned long long s_tot[kAccWords];
+    pdl_wait();   // the previous launch of the stream is complete before anything of this one becomes visible
+    scratch_flush(sc, G.ctl->acc, tid);
+    __threadfence();  // this CTA's atomics are ordered before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&G.ctl->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last)
+        return;
+    // ---- last CTA of this device ----
+    __threadfence();
+    if (threadIdx.x < kAccWords)
+        s_tot[threadIdx.x] = atomicExch(&G.ctl->acc[threadIdx.x], 0ull);
+    if (threadIdx.x == 0) {
+        G.ctl->next = 0u;
+        G.ctl->ticket = 0u;
+    }
+    __syncthreads();
     if (G.peer.world > 1)
-        peer_combine(acc, G.peer);
+        peer_exchange(s_tot, G.peer);
+    if (G.peer.world > 1 && G.peer.mode == kPeerPush)
+        return;   // the totals are in the mailboxes; peer_pull_kernel delivers them
+    if (out != nullptr && threadIdx.x < kAccWords && s_tot[threadIdx.x] != 0ull)
+        atomicAdd(out + threadIdx.x, s_tot[threadIdx.x]);
+    if (G.host_slot != nullptr && threadIdx.x < kPeerHalves)
+        st_relaxed_sys(G.host_slot + threadIdx.x, flagged_half(s_tot, threadIdx.x, G.host_flag));
+}
+
+// One chunk of the job: thread t owns units base + k * 256 + t for k < rounds, in that order, and accumulates value
+// and value^2 in W::Real (short runs: at most rounds * kUnitPaths <= 384 terms) before the fp64 block reduction.
+template <class W>
+__device__ __forceinline__ void run_chunk(const typename W::Params &P, const JobGeometry &G, unsigned long long chunk, int tid,
+                                          const typename W::Shared &sh, typename W::Real &s_out, typename W::Real &s2_out,
+                                          unsigned long long &n_valid)
+{
+    using Real = typename W::Real;
+    const unsigned long long base = chunk * G.chunk_units;
+    const unsigned long long path_end = (base + G.chunk_units) * (unsigned long long)W::kUnitPaths;
+    Real s = 0, s2 = 0;
+    const bool whole = path_end <= G.total_paths;
+    if (whole) {
+        n_valid = G.chunk_units * (unsigned long long)W::kUnitPaths;
+    } else {
+        const unsigned long long path0 = base * (unsigned long long)W::kUnitPaths;
+        n_valid = G.total_paths > path0 ? G.total_paths - path0 : 0ull;
+    }
+    if (whole || W::kUnitPaths == 1) {
+        // one path per unit: the same loop serves the job's last (partial) chunk, so the
+        // (large) estimator body is instantiated once
+#pragma unroll W::kUnroll
+        for (int k = 0; k < G.rounds; k++) {
+            const unsigned long long unit = base + (unsigned long long)k * kThreads + tid;
+            if (W::kUnitPaths == 1 && !whole && unit >= G.total_paths)
+                break;
+            Real v[W::kUnitPaths];
+            W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh);
+#pragma unroll
+            for (int q = 0; q < W::kUnitPaths; q++) {
+                s += v[q];
+                s2 = fma(v[q], v[q], s2);
+            }
+        }
+    } else {
+        // the job's last chunk with several paths per unit: mask paths beyond the total
+#pragma unroll 1
+        for (int k = 0; k < G.rounds; k++) {
+            const unsigned long long unit = base + (unsigned long long)k * kThreads + tid;
+            if (unit * (unsigned long long)W::kUnitPaths >= G.total_paths)
+                break;
+            Real v[W::kUnitPaths];
+            W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh);
+#pragma unroll
+            for (int q = 0; q < W::kUnitPaths; q++) {
+                if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths) {
+                    s += v[q];
+                    s2 = fma(v[q], v[q], s2);
+                }
+            }
+        }
+    }
+    s_out = s;
+    s2_out = s2;
 }
 
 // The pricing kernel skeleton.  W is a workload policy:
@@ -266,9 +442,7 @@ __device__ __forceinline__ void finish(const BlockScratch &sc, unsigned long lon
 //   W::eval(P, unit_lo, unit_hi, v, sh) fills v[kUnitPaths] with the per-path values of a draw unit;
 //                      inside a chunk unit_hi is the same for every thread (chunks are aligned), so the
 //                      part of the first two Philox rounds that depends only on it runs on the uniform datapath
-// A CTA walks chunks first_chunk + blockIdx.x, + gridDim.x, ...; thread t of a chunk owns units
-// base + k * 256 + t for k < rounds, in that order, and accumulates value and value^2 in W::Real
-// (short runs: at most rounds * kUnitPaths <= 384 terms) before the fp64 block reduction.
+// Persistent CTAs; every sub-block of 256 threads walks chunks of the shard (ChunkWalk) through run_chunk.
 template <class W>
 __global__ void __launch_bounds__(kThreads * W::kSubBlocks, W::kMinBlocks)
 mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_constant__ Geometry G,
@@ -276,6 +450,7 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
 {
     using Real = typename W::Real;
     constexpr int kSub = W::kSubBlocks;
+    pdl_launch_dependents();
     // W::Shared in dynamic shared memory (the replicated fp64 tables are 96 KB); nothing for fp32
     extern __shared__ __align__(16) unsigned char mcb_dynamic_smem[];
     typename W::Shared &sh = *reinterpret_cast<typename W::Shared *>(mcb_dynamic_smem);
@@ -288,67 +463,114 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
     if (tid < kAccWords)
         sc.acc[tid] = 0ull;
     __syncthreads();
-    const unsigned long long last = G.first_chunk + G.n_chunks;
-    const unsigned long long stride = (unsigned long long)gridDim.x * kSub;
-    for (unsigned long long chunk = G.first_chunk + (unsigned long long)blockIdx.x * kSub + sub; chunk < last; chunk += stride) {
-        const unsigned long long base = chunk * G.chunk_units;
-        const unsigned long long path_end = (base + G.chunk_units) * (unsigned long long)W::kUnitPaths;
-        Real s = 0, s2 = 0;
+    for (ChunkWalk<kSub> walk(sub); walk.live(G); walk.advance(sc)) {
+        walk.claim_ahead(G, tid);
+        Real s, s2;
         unsigned long long n_valid;
-        const bool whole = path_end <= G.total_paths;
-        if (whole) {
-            n_valid = G.chunk_units * (unsigned long long)W::kUnitPaths;
-        } else {
-            const unsigned long long path0 = base * (unsigned long long)W::kUnitPaths;
-            n_valid = G.total_paths > path0 ? G.total_paths - path0 : 0ull;
-        }
-        if (whole || W::kUnitPaths == 1) {
-            // one path per unit: the same loop serves the job's last (partial) chunk, so the
-            // (large) estimator body is instantiated once
-#pragma unroll W::kUnroll
-            for (int k = 0; k < G.rounds; k++) {
-                const unsigned long long unit = base + (unsigned long long)k * kThreads + tid;
-                if (W::kUnitPaths == 1 && !whole && unit >= G.total_paths)
-                    break;
-                Real v[W::kUnitPaths];
-                W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh);
-#pragma unroll
-                for (int q = 0; q < W::kUnitPaths; q++) {
-                    s += v[q];
-                    s2 = fma(v[q], v[q], s2);
-                }
-            }
-        } else {
-            // the job's last chunk with several paths per unit: mask paths beyond the total
-#pragma unroll 1
-            for (int k = 0; k < G.rounds; k++) {
-                const unsigned long long unit = base + (unsigned long long)k * kThreads + tid;
-                if (unit * (unsigned long long)W::kUnitPaths >= G.total_paths)
-                    break;
-                Real v[W::kUnitPaths];
-                W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh);
-#pragma unroll
-                for (int q = 0; q < W::kUnitPaths; q++) {
-                    if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths) {
-                        s += v[q];
-                        s2 = fma(v[q], v[q], s2);
-                    }
-                }
-            }
-        }
-        chunk_commit<kSub>((double)s, (double)s2, n_valid, G, sc, sub, tid);
+        run_chunk<W>(P, G, G.first_chunk + walk.chunk, tid, sh, s, s2, n_valid);
+        chunk_commit<kSub>((double)s, (double)s2, n_valid, G, sc, sub, tid, walk.ahead);
     }
     if constexpr (kSub > 1)
         __syncthreads();  // every sub-block has committed its last chunk before the CTA-wide tail
     finish(sc, acc, G, tid);
 }
 
+// ---- many jobs in ONE launch (sweeps) -------------------------------------------------------------
+// The reference's cvaOpt driver prices 5 time grids x 4 thread counts as 20 blocking calls
+// (double_precision/cvaOpt.cu:70-109).  Here the jobs of a sweep that share a kernel (workload and precision) are
+// laid end to end in one chunk index space; a sub-block claims global chunks from one counter, finds the job a chunk
+// belongs to (jobs are few: a linear scan of the offsets) and runs it exactly as the one-job kernel would -- same
+// chunks, same reduction, same integer limbs, so every job's result is bit-identical to its one-call price.  A job's
+// parameters are read from the kernel's parameter block through a job index (constant bank, one indexed load per
+// use), its limbs go to its own 12 words of `acc`, and the launch's last CTA publishes all of them to the host.
+constexpr int kBatchMaxJobs = 24;
+template <class W>
+struct BatchJobs {
+    int n_jobs;
+    int pad;
+    LaunchCtl *ctl;
+    unsigned long long *acc;              // n_jobs x 12 words of device scratch, zero between launches
+    unsigned long long *host_slots;       // n_jobs x kPeerSlotWords words of mapped host memory (flagged halves)
+    unsigned long long host_flag;
+    unsigned int first[kBatchMaxJobs + 1];    // global index of each job's first chunk; first[n_jobs] = total
+    unsigned short slot[kBatchMaxJobs];       // which host slot a job reports to
+    JobGeometry geo[kBatchMaxJobs];
+    typename W::Params params[kBatchMaxJobs];
+};
+
+template <class W>
+__global__ void __launch_bounds__(kThreads * W::kSubBlocks, W::kMinBlocks)
+mc_accumulate_batch_kernel(const __grid_constant__ BatchJobs<W> B)
+{
+    using Real = typename W::Real;
+    constexpr int kSub = W::kSubBlocks;
+    pdl_launch_dependents();
+    extern __shared__ __align__(16) unsigned char mcb_dynamic_smem[];
+    typename W::Shared &sh = *reinterpret_cast<typename W::Shared *>(mcb_dynamic_smem);
+    __shared__ BlockScratch scs[kSub];
+    __shared__ bool s_last;
+    const int sub = kSub == 1 ? 0 : (int)(threadIdx.x / kThreads);
+    const int tid = kSub == 1 ? (int)threadIdx.x : (int)(threadIdx.x % kThreads);
+    BlockScratch &sc = scs[sub];
+    sh.load();
+    if (tid < kAccWords)
+        sc.acc[tid] = 0ull;
+    __syncthreads();
+    const unsigned int total = B.first[B.n_jobs];
+    unsigned int chunk = blockIdx.x * kSub + sub, ahead = 0u;
+    int job = 0;
+    while (chunk < total) {
+        if (tid == 0)
+            ahead = gridDim.x * kSub + atomicAdd(&B.ctl->next, 1u);
+        // chunks are claimed in increasing order, so the job index only moves forward; when it moves, the limbs
+        // collected so far belong to the previous job
+        int j = job;
+        while (chunk >= B.first[j + 1])
+            j++;
+        if (j != job) {
+            // (thread t < 12 reads and clears its own word; thread 0's next write to sc.acc comes after a barrier)
+            scratch_flush(sc, B.acc + (size_t)job * kAccWords, tid);
+            if (tid < kAccWords)
+                sc.acc[tid] = 0ull;
+            job = j;
+        }
+        Real s, s2;
+        unsigned long long n_valid;
+        run_chunk<W>(B.params[job], B.geo[job], (unsigned long long)(chunk - B.first[job]), tid, sh, s, s2, n_valid);
+        chunk_commit<kSub>((double)s, (double)s2, n_valid, B.geo[job], sc, sub, tid, ahead);
+        chunk = sc.next;
+    }
+    pdl_wait();
+    scratch_flush(sc, B.acc + (size_t)job * kAccWords, tid);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&B.ctl->ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        B.ctl->next = 0u;
+        B.ctl->ticket = 0u;
+    }
+    // every job's 24 flagged halves to its host slot; the device scratch is left zeroed
+    for (int i = threadIdx.x; i < B.n_jobs * kPeerHalves; i += blockDim.x) {
+        const int jb = i / kPeerHalves, h = i % kPeerHalves;
+        unsigned long long *word = B.acc + (size_t)jb * kAccWords + (h >> 1);
+        const unsigned long long w = *((volatile unsigned long long *)word);
+        st_relaxed_sys(B.host_slots + (size_t)B.slot[jb] * kPeerSlotWords + h, B.host_flag | ((h & 1) ? (w >> 32) : (w & 0xffffffffull)));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B.n_jobs * kAccWords; i += blockDim.x)
+        B.acc[i] = 0ull;
+}
+
 // Host side of a launch: dynamic shared memory = W::Shared (opt-in above 48 KB, set once per instantiation).
 template <class W> constexpr size_t accumulate_smem_bytes() { return std::is_empty<typename W::Shared>::value ? 0 : sizeof(typename W::Shared); }
-template <class W> inline cudaError_t accumulate_prepare()
+template <class W, class Kernel> inline cudaError_t accumulate_prepare(Kernel kernel, bool *done)
 {
     // a function attribute is per device: set it once on each device this process prices on
-    static bool done[64] = {};
     if (accumulate_smem_bytes<W>() <= 48 * 1024)
         return cudaSuccess;
     int device = 0;
@@ -356,29 +578,81 @@ template <class W> inline cudaError_t accumulate_prepare()
     if (e != cudaSuccess || device < 0 || device >= 64)
         return e != cudaSuccess ? e : cudaErrorInvalidDevice;
     if (!done[device]) {
-        e = cudaFuncSetAttribute(mc_accumulate_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)accumulate_smem_bytes<W>());
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)accumulate_smem_bytes<W>());
         if (e != cudaSuccess)
             return e;
         done[device] = true;
     }
     return cudaSuccess;
 }
+template <class W> inline cudaError_t accumulate_prepare()
+{
+    static bool done[64] = {};
+    return accumulate_prepare<W>(mc_accumulate_kernel<W>, done);
+}
+template <class W> inline cudaError_t accumulate_batch_prepare()
+{
+    static bool done[64] = {};
+    return accumulate_prepare<W>(mc_accumulate_batch_kernel<W>, done);
+}
+
+// launch with or without programmatic dependent launch (the attribute lets this kernel start while the previous one
+// of the stream drains; see pdl_launch_dependents)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, bool overlap,
+                                 Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// per-launch options the engine passes down to the launchers
+struct LaunchOptions {
+    bool overlap = false;   // programmatic dependent launch
+};
+
 template <class W>
 inline cudaError_t accumulate_launch(int grid, const typename W::Params &p, const Geometry &g, unsigned long long *d_acc,
-                                     cudaStream_t stream)
+                                     cudaStream_t stream, const LaunchOptions &opt = LaunchOptions())
 {
     cudaError_t e = accumulate_prepare<W>();
     if (e != cudaSuccess)
         return e;
-    mc_accumulate_kernel<W><<<grid, kThreads * W::kSubBlocks, accumulate_smem_bytes<W>(), stream>>>(p, g, d_acc);
-    return cudaGetLastError();
+    return launch_kernel(mc_accumulate_kernel<W>, grid, kThreads * W::kSubBlocks, accumulate_smem_bytes<W>(), stream, opt.overlap,
+                         p, g, d_acc);
+}
+template <class W>
+inline cudaError_t accumulate_batch_launch(int grid, const BatchJobs<W> &b, cudaStream_t stream, const LaunchOptions &opt = LaunchOptions())
+{
+    cudaError_t e = accumulate_batch_prepare<W>();
+    if (e != cudaSuccess)
+        return e;
+    return launch_kernel(mc_accumulate_batch_kernel<W>, grid, kThreads * W::kSubBlocks, accumulate_smem_bytes<W>(), stream, opt.overlap, b);
 }
 template <class W> inline int accumulate_blocks_per_sm()
 {
     int n = 0;
     if (accumulate_prepare<W>() != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mc_accumulate_kernel<W>, kThreads * W::kSubBlocks,
+                                                      accumulate_smem_bytes<W>()) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+template <class W> inline int accumulate_batch_blocks_per_sm()
+{
+    int n = 0;
+    if (accumulate_batch_prepare<W>() != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mc_accumulate_batch_kernel<W>, kThreads * W::kSubBlocks,
                                                       accumulate_smem_bytes<W>()) != cudaSuccess)
         return 0;
     return n;

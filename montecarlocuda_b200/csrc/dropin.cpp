@@ -74,6 +74,8 @@ Global &engine()
         const int st = mcb200_create(&ctx, first + i);
         if (st != MCB200_OK)
             die("mcb200_create", st, nullptr);
+        if (g.verbose)
+            mcb200_set_option(ctx, MCB200_OPT_TIMING, 1);  // the kernel time printed below
         g.ctxs.push_back(ctx);
     }
     g.ready = true;

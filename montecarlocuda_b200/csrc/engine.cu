@@ -5,35 +5,56 @@
 // cvaMonteCarlo / MonteCarlo_closing and the three extern "C" wrappers
 // (DP/MonteCarloKernel.cu:296-532).  The reference allocates device + pinned memory, seeds
 // 65 536 XORWOW states, copies parameters into __constant__ symbols, prints timing lines and
-// frees everything on EVERY call; here a context owns a stream, a 96-byte device accumulator and
-// its pinned mirror for its whole life, the generator is stateless, and a call is
-// memset -> one kernel -> 96-byte copy.
+// frees everything on EVERY call; here a context owns a stream, a ring of self-cleaning launch control blocks
+// and a few result slots in mapped host memory for its whole life, the generator is stateless, and a blocking
+// call is ONE kernel launch: no memset in front of it (the launch's last CTA leaves the control block zeroed),
+// no copy and no stream synchronisation behind it (that CTA writes the 96-byte result into the host slot as
+// flagged words and the host polls the flags), no events unless the caller asked for kernel times.
 #include "../../include/mcb200.h"
 
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
 #include <vector>
 
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#endif
+
 #include "launch.h"
 
 using namespace mcb;
+
+constexpr int kCtlRing = 8;     // launch control blocks: a launch may still be draining when the next ones start
+constexpr int kHostRing = 4;    // result slots of the blocking calls
 
 struct mcb200_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    unsigned long long *d_acc = nullptr;
+    unsigned long long *d_acc = nullptr;  // debug_reduce
     unsigned long long *h_acc = nullptr;  // pinned
-    // accumulators of a batch (mcb200_price_batch): grown on demand, kept for the context's life
-    unsigned long long *d_batch = nullptr, *h_batch = nullptr;
+    LaunchCtl *d_ctl = nullptr;                  // kCtlRing blocks, zero between launches
+    unsigned long long *d_batch_acc = nullptr;   // kCtlRing x kBatchMaxJobs x 12 words, zero between launches
+    unsigned long long *h_slots = nullptr;       // mapped pinned: kHostRing result slots of kPeerSlotWords words
+    unsigned long long *d_slots = nullptr;       // ... as the device addresses them
+    // result slots of a batch (mcb200_price_batch): grown on demand, kept for the context's life
+    unsigned long long *h_batch_slots = nullptr, *d_batch_slots = nullptr;
     size_t batch_capacity = 0;  // in jobs
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::string last_error;
     uint64_t launches = 0;
+    uint64_t results = 0;       // blocking results delivered through a host slot (flag = peer_flag(results))
+    bool timing = false;        // record CUDA events around the kernels of the blocking calls (kernel_ms)
+    bool overlap = false;       // programmatic dependent launch: consecutive launches of a stream overlap their tails
+    cudaStream_t last_stream = nullptr;
+    bool launched = false;
     std::mutex mu;
     mcb200_peer *peer = nullptr;  // attached peer group: sharded launches combine inside the kernel
 };
@@ -42,13 +63,44 @@ struct mcb200_ctx {
 struct mcb200_peer {
     mcb200_ctx *ctx = nullptr;
     int rank = 0, world = 1;
+    int mode = kPeerWait;
+    unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
     unsigned long long *mailbox = nullptr;          // this rank's mailbox (device memory of ctx->device)
-    unsigned int *ticket = nullptr;
     unsigned long long *mail[kPeerMax] = {};        // every rank's mailbox as addressed from this device
     bool opened[kPeerMax] = {};                     // mail[r] came from cudaIpcOpenMemHandle
     bool connected = false;
     unsigned long long seq = 0;                     // fused launches so far
 };
+
+// The second phase of a kPeerPush launch, when somebody wants the totals: one small CTA sums the `world` sources of
+// launch `seq` out of this device's mailbox into out[12] (device memory: overwritten, not added to).
+__global__ void __launch_bounds__(kThreads)
+peer_pull_kernel(const unsigned long long *mailbox, int world, unsigned long long seq, unsigned long long timeout_ns,
+                 unsigned long long *out)
+{
+    __shared__ unsigned int s_bad;
+    __shared__ unsigned int s_half[kPeerMax * kPeerHalves];
+    const int tid = threadIdx.x;
+    if (tid == 0)
+        s_bad = 0u;
+    __syncthreads();
+    if (tid < kPeerHalves * world) {
+        unsigned int v;
+        if (peer_poll(mailbox, seq, tid / kPeerHalves, tid % kPeerHalves, timeout_ns, v) != 0)
+            atomicAdd(&s_bad, 1u);
+        s_half[tid] = v;
+    }
+    __syncthreads();
+    if (tid < kAccWords) {
+        unsigned long long total = 0ull;
+        for (int src = 0; src < world; src++)
+            total += (unsigned long long)s_half[src * kPeerHalves + 2 * tid] |
+                     ((unsigned long long)s_half[src * kPeerHalves + 2 * tid + 1] << 32);
+        if (tid == kAccWords - 1 && s_bad)
+            total += kErrPeerTimeout;
+        out[tid] = total;
+    }
+}
 
 namespace {
 
@@ -156,16 +208,23 @@ int fill_plan(int workload, int precision, uint64_t n_paths, double scale_ref, d
     return MCB200_OK;
 }
 
-Geometry make_geometry(const mcb200_plan_t &plan, uint64_t first_chunk, uint64_t n_chunks)
+JobGeometry job_geometry(const mcb200_plan_t &plan)
 {
-    Geometry g{};
+    JobGeometry g{};
     g.total_paths = plan.total_paths;
     g.chunk_units = plan.chunk_units;
-    g.first_chunk = first_chunk;
-    g.n_chunks = n_chunks;
     g.rounds = plan.rounds;
     g.scale_exp_sum = plan.scale_exp_sum;
     g.scale_exp_sumsq = plan.scale_exp_sumsq;
+    return g;
+}
+
+Geometry make_geometry(const mcb200_plan_t &plan, uint64_t first_chunk, uint64_t n_chunks)
+{
+    Geometry g{};
+    static_cast<JobGeometry &>(g) = job_geometry(plan);
+    g.first_chunk = first_chunk;
+    g.n_chunks = n_chunks;
     return g;
 }
 
@@ -317,8 +376,10 @@ int make_cva_job(int precision, const mcb200_cva_t *c, uint64_t seed, CvaTables 
             d.kd = o.k;
         }
     }
-    if (!(std::fabs(std::log(o.s / o.k)) + n * (std::fabs((o.r - 0.5 * o.v * o.v) * dt) + 9.0 * o.v * std::sqrt(dt)) < 700.0))
-        return MCB200_ERR_INVALID;  // range of the table-driven exponential
+    // range of the table-driven exponential: |ln(s/K)| + |drift| T + 9 standard deviations of the log-spot at maturity
+    // (the sum of n steps, not n times one step's reach: that rejected valid high-volatility jobs with many dates)
+    if (!(std::fabs(std::log(o.s / o.k)) + std::fabs((o.r - 0.5 * o.v * o.v) * o.t) + 9.0 * o.v * std::sqrt(o.t) < 700.0))
+        return MCB200_ERR_INVALID;
     t->job.keys = make_keys(seed);
     t->job.y0 = std::log(o.s / o.k);
     t->job.mu_dt = (o.r - 0.5 * o.v * o.v) * dt;  // geomBrownian, DP/MonteCarloKernel.cu:104-107
@@ -356,40 +417,123 @@ int blocks_per_sm(const mcb200_plan_t &plan, const AnyJob &job)
     }
 }
 
+// where a launch's result goes
+struct Sink {
+    unsigned long long *d_acc = nullptr;      // device accumulator block the launch adds its totals to, or nullptr
+    unsigned long long *host_slot = nullptr;  // device address of a mapped host slot, or nullptr
+    unsigned long long host_flag = 0;
+    bool fused = false;                       // run the attached peer group's exchange in the kernel's tail
+};
+
+// a context's launches normally arrive on one stream; when the caller switches streams, the control blocks of
+// launches still in flight on the old one must not be reused under them
+void order_streams(mcb200_ctx *ctx, cudaStream_t stream)
+{
+    if (ctx->launched && ctx->last_stream != stream) {
+        if (cudaStreamSynchronize(ctx->last_stream) != cudaSuccess)
+            cudaGetLastError();  // the old stream is gone: nothing of it can still be running
+    }
+    ctx->last_stream = stream;
+    ctx->launched = true;
+}
+
 // enqueue one shard on `stream` (device already current)
 int enqueue(mcb200_ctx *ctx, const mcb200_plan_t &plan, const AnyJob &job, uint64_t first_chunk,
-            uint64_t n_chunks, unsigned long long *d_acc, cudaStream_t stream, bool fused = false)
+            uint64_t n_chunks, const Sink &sink, cudaStream_t stream)
 {
-    mcb200_peer *peer = fused ? ctx->peer : nullptr;
-    if (n_chunks == 0 && !peer)
+    mcb200_peer *peer = sink.fused ? ctx->peer : nullptr;
+    if (n_chunks == 0 && !peer && !sink.host_slot)
         return MCB200_OK;
     int per_sm = blocks_per_sm(plan, job);
     if (per_sm < 1)
         return fail(ctx, MCB200_ERR_CUDA, "kernel cannot be resident on this device (occupancy 0)");
-    uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
-    if (grid > n_chunks)
-        grid = n_chunks;
-    if (grid == 0)
-        grid = 1;  // an empty shard still takes part in the fused combine
-    Geometry g = make_geometry(plan, first_chunk, n_chunks);
-    if (peer) {
-        g.peer.world = peer->world;
-        g.peer.rank = peer->rank;
-        g.peer.seq = ++peer->seq;
-        for (int r = 0; r < peer->world; r++)
-            g.peer.mail[r] = peer->mail[r];
-        g.peer.ticket = peer->ticket;
-    }
-    cudaError_t e;
-    switch (plan.workload) {
-        case MCB200_VANILLA: e = vanilla_launch(plan.precision, job.vanilla, g, (int)grid, d_acc, stream); break;
-        case MCB200_BASKET: e = basket_launch(plan.precision, job.basket.job, g, (int)grid, d_acc, stream); break;
-        default: e = cva_launch(plan.precision, job.cva.job, g, (int)grid, d_acc, stream); break;
-    }
-    if (e != cudaSuccess)
-        return fail_cuda(ctx, e, "kernel launch");
-    ctx->launches++;
+    order_streams(ctx, stream);
+    // a launch claims chunks through a 32-bit counter: longer shards go out as several launches (their totals add up:
+    // integer limbs); only the last one carries the exchange / the host slot
+    constexpr uint64_t kMaxChunks = 1ull << 30;
+    if ((peer || sink.host_slot) && n_chunks > kMaxChunks)
+        return fail(ctx, MCB200_ERR_UNSUPPORTED, "more than 2^30 chunks in one shard of a blocking or fused launch");
+    do {
+        const uint64_t part = n_chunks > kMaxChunks ? kMaxChunks : n_chunks;
+        const bool final_part = part == n_chunks;
+        uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
+        if (grid > part)
+            grid = part;
+        if (grid == 0)
+            grid = 1;  // an empty shard still takes part in the fused combine / still answers its host slot
+        Geometry g = make_geometry(plan, first_chunk, part);
+        g.ctl = ctx->d_ctl + (ctx->launches % kCtlRing);
+        if (final_part) {
+            g.host_slot = sink.host_slot;
+            g.host_flag = sink.host_flag;
+        }
+        if (peer && final_part) {
+            g.peer.world = peer->world;
+            g.peer.rank = peer->rank;
+            g.peer.mode = peer->mode;
+            g.peer.seq = peer->seq + 1;
+            g.peer.timeout_ns = peer->timeout_ns;
+            for (int r = 0; r < peer->world; r++)
+                g.peer.mail[r] = peer->mail[r];
+        }
+        LaunchOptions opt;
+        opt.overlap = ctx->overlap;
+        cudaError_t e;
+        switch (plan.workload) {
+            case MCB200_VANILLA: e = vanilla_launch(plan.precision, job.vanilla, g, (int)grid, sink.d_acc, stream, opt); break;
+            case MCB200_BASKET: e = basket_launch(plan.precision, job.basket.job, g, (int)grid, sink.d_acc, stream, opt); break;
+            default: e = cva_launch(plan.precision, job.cva.job, g, (int)grid, sink.d_acc, stream, opt); break;
+        }
+        if (e != cudaSuccess)
+            return fail_cuda(ctx, e, "kernel launch");
+        ctx->launches++;
+        if (peer && final_part)
+            peer->seq++;  // only a launch that went out counts: a failed one must not desynchronise the ranks
+        first_chunk += part;
+        n_chunks -= part;
+    } while (n_chunks > 0);
     return MCB200_OK;
+}
+
+inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    _mm_pause();
+#endif
+}
+
+// Wait for the 24 flagged halves of a host slot (written by a launch's last CTA over PCIe) and assemble the 12 words.
+// No stream synchronisation: the slot IS the completion signal.  The stream is only queried now and then, so that a
+// launch that died ends as an error instead of an endless poll.
+int wait_slot(mcb200_ctx *ctx, cudaStream_t stream, const unsigned long long *slot, unsigned long long flag,
+              uint64_t acc[MCB200_ACC_WORDS])
+{
+    const volatile unsigned long long *w = slot;
+    bool drained = false;
+    for (uint64_t spin = 1;; spin++) {
+        int h = 0;
+        unsigned long long v[kPeerHalves];
+        for (; h < kPeerHalves; h++) {
+            v[h] = w[h];
+            if ((v[h] & 0xffffffff00000000ull) != flag)
+                break;
+        }
+        if (h == kPeerHalves) {
+            for (int i = 0; i < MCB200_ACC_WORDS; i++)
+                acc[i] = (v[2 * i] & 0xffffffffull) | ((v[2 * i + 1] & 0xffffffffull) << 32);
+            return MCB200_OK;
+        }
+        if (drained)
+            return fail(ctx, MCB200_ERR_CUDA, "the launch finished without publishing its result");
+        if ((spin & 0x3fff) == 0) {
+            const cudaError_t e = cudaStreamQuery(stream);
+            if (e == cudaSuccess)
+                drained = true;  // everything has run: one more look at the slot, then give up
+            else if (e != cudaErrorNotReady)
+                return fail_cuda(ctx, e, "pricing kernel");
+        }
+        cpu_relax();
+    }
 }
 
 // one-call pricing over n_ctx devices of this process
@@ -397,49 +541,81 @@ int price(mcb200_ctx **ctxs, int n_ctx, const mcb200_plan_t &plan, const AnyJob 
 {
     if (!ctxs || n_ctx < 1 || !out)
         return MCB200_ERR_INVALID;
-    for (int i = 0; i < n_ctx; i++)
+    for (int i = 0; i < n_ctx; i++) {
         if (!ctxs[i])
             return MCB200_ERR_INVALID;
+        for (int j = 0; j < i; j++)
+            if (ctxs[j] == ctxs[i])
+                return fail(ctxs[i], MCB200_ERR_INVALID, "the same context appears twice in the list");
+    }
+    // lock in one canonical order (by address), whatever order the caller listed the contexts in: two calls with
+    // overlapping lists cannot deadlock each other
+    std::vector<mcb200_ctx *> order(ctxs, ctxs + n_ctx);
+    std::sort(order.begin(), order.end());
     std::vector<std::unique_lock<std::mutex>> locks;
-    for (int i = 0; i < n_ctx; i++)
-        locks.emplace_back(ctxs[i]->mu);
+    for (mcb200_ctx *c : order)
+        locks.emplace_back(c->mu);
     // enqueue everywhere first, then wait: the devices run concurrently
-    for (int i = 0; i < n_ctx; i++) {
+    int status = MCB200_OK, enqueued = 0;
+    std::vector<unsigned long long> flags((size_t)n_ctx);
+    std::vector<int> slots((size_t)n_ctx);
+    for (int i = 0; i < n_ctx && status == MCB200_OK; i++) {
         mcb200_ctx *ctx = ctxs[i];
         DeviceGuard guard(ctx->device);
-        MCB_CUDA(ctx, guard.status());
-        uint64_t first, count;
-        int st = mcb200_shard_range(&plan, i, n_ctx, &first, &count);
-        if (st != MCB200_OK)
-            return st;
-        MCB_CUDA(ctx, cudaMemsetAsync(ctx->d_acc, 0, sizeof(unsigned long long) * kAccWords, ctx->stream));
-        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
-        st = enqueue(ctx, plan, job, first, count, ctx->d_acc, ctx->stream);
-        if (st != MCB200_OK)
-            return st;
-        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
-        MCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_acc, ctx->d_acc, sizeof(unsigned long long) * kAccWords,
-                                      cudaMemcpyDeviceToHost, ctx->stream));
+        uint64_t first = 0, count = 0;
+        if (guard.status() != cudaSuccess)
+            status = fail_cuda(ctx, guard.status(), "cudaSetDevice");
+        if (status == MCB200_OK)
+            status = mcb200_shard_range(&plan, i, n_ctx, &first, &count);
+        if (status == MCB200_OK && ctx->timing && cudaEventRecord(ctx->ev_begin, ctx->stream) != cudaSuccess)
+            status = fail_cuda(ctx, cudaGetLastError(), "cudaEventRecord");
+        if (status == MCB200_OK) {
+            const uint64_t seq = ++ctx->results;
+            slots[i] = (int)(seq % kHostRing);
+            flags[i] = peer_flag(seq);
+            Sink sink;
+            sink.host_slot = ctx->d_slots + (size_t)slots[i] * kPeerSlotWords;
+            sink.host_flag = flags[i];
+            status = enqueue(ctx, plan, job, first, count, sink, ctx->stream);
+        }
+        if (status == MCB200_OK && ctx->timing && cudaEventRecord(ctx->ev_end, ctx->stream) != cudaSuccess)
+            status = fail_cuda(ctx, cudaGetLastError(), "cudaEventRecord");
+        if (status == MCB200_OK)
+            enqueued = i + 1;
     }
     uint64_t total[MCB200_ACC_WORDS] = {0};
     double kernel_ms = 0;
-    for (int i = 0; i < n_ctx; i++) {
+    for (int i = 0; i < enqueued; i++) {
         mcb200_ctx *ctx = ctxs[i];
         DeviceGuard guard(ctx->device);
-        MCB_CUDA(ctx, guard.status());
-        MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        float ms = 0;
-        MCB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
-        if (ms > kernel_ms)
-            kernel_ms = ms;
+        if (status != MCB200_OK) {
+            cudaStreamSynchronize(ctx->stream);  // an error on another device: do not leave kernels in flight behind it
+            continue;
+        }
+        uint64_t part[MCB200_ACC_WORDS];
+        status = wait_slot(ctx, ctx->stream, ctx->h_slots + (size_t)slots[i] * kPeerSlotWords, flags[i], part);
+        if (status != MCB200_OK)
+            continue;
+        if (ctx->timing) {
+            float ms = 0;
+            if (cudaEventSynchronize(ctx->ev_end) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) {
+                if (ms > kernel_ms)
+                    kernel_ms = ms;
+            } else {
+                cudaGetLastError();
+            }
+        }
         for (int w = 0; w < MCB200_ACC_WORDS; w++)
-            total[w] += ctx->h_acc[w];  // exact: integer limbs with 31 bits of headroom
+            total[w] += part[w];  // exact: integer limbs with 31 bits of headroom
     }
+    if (status != MCB200_OK)
+        return status;
     int st = mcb200_finalize(&plan, total, out);
     out->kernel_ms = kernel_ms;
     if (st != MCB200_OK)
         return fail(ctxs[0], st, st == MCB200_ERR_OVERFLOW ? "partial sum outside the fixed-point window or NaN"
-                                                           : "path count mismatch");
+                                                           : st == MCB200_ERR_PEER_TIMEOUT ? "a peer rank did not deliver its partial sums in time"
+                                                                                            : "path count mismatch");
     return MCB200_OK;
 }
 
@@ -513,17 +689,29 @@ int mcb200_create(mcb200_ctx **out, int device)
     ctx->device = device;
     DeviceGuard guard(device);
     cudaDeviceProp prop;
+    const size_t ctl_bytes = sizeof(LaunchCtl) * kCtlRing;
+    const size_t batch_acc_bytes = sizeof(unsigned long long) * kAccWords * kBatchMaxJobs * kCtlRing;
+    const size_t slot_bytes = sizeof(unsigned long long) * kPeerSlotWords * kHostRing;
     bool ok = guard.status() == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&ctx->d_acc, sizeof(unsigned long long) * kAccWords) == cudaSuccess &&
               cudaMallocHost(&ctx->h_acc, sizeof(unsigned long long) * kAccWords) == cudaSuccess &&
-              cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
+              cudaMalloc(&ctx->d_ctl, ctl_bytes) == cudaSuccess && cudaMemset(ctx->d_ctl, 0, ctl_bytes) == cudaSuccess &&
+              cudaMalloc(&ctx->d_batch_acc, batch_acc_bytes) == cudaSuccess &&
+              cudaMemset(ctx->d_batch_acc, 0, batch_acc_bytes) == cudaSuccess &&
+              cudaHostAlloc(&ctx->h_slots, slot_bytes, cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer(&ctx->d_slots, ctx->h_slots, 0) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess &&
+              cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         mcb200_destroy(ctx);
         return MCB200_ERR_CUDA;
     }
+    std::memset(ctx->h_slots, 0, slot_bytes);
     ctx->sm_count = prop.multiProcessorCount;
+    const char *env = std::getenv("MCB200_OVERLAP");
+    ctx->overlap = env && env[0] == '1';
     *out = ctx;
     return MCB200_OK;
 }
@@ -536,6 +724,8 @@ int mcb200_destroy(mcb200_ctx *ctx)
         DeviceGuard guard(ctx->device);
         if (ctx->stream)
             cudaStreamSynchronize(ctx->stream);
+        if (ctx->launched && ctx->last_stream != ctx->stream && cudaStreamSynchronize(ctx->last_stream) != cudaSuccess)
+            cudaGetLastError();
         if (ctx->ev_begin)
             cudaEventDestroy(ctx->ev_begin);
         if (ctx->ev_end)
@@ -544,10 +734,14 @@ int mcb200_destroy(mcb200_ctx *ctx)
             cudaFree(ctx->d_acc);
         if (ctx->h_acc)
             cudaFreeHost(ctx->h_acc);
-        if (ctx->d_batch)
-            cudaFree(ctx->d_batch);
-        if (ctx->h_batch)
-            cudaFreeHost(ctx->h_batch);
+        if (ctx->d_ctl)
+            cudaFree(ctx->d_ctl);
+        if (ctx->d_batch_acc)
+            cudaFree(ctx->d_batch_acc);
+        if (ctx->h_slots)
+            cudaFreeHost(ctx->h_slots);
+        if (ctx->h_batch_slots)
+            cudaFreeHost(ctx->h_batch_slots);
         if (ctx->stream)
             cudaStreamDestroy(ctx->stream);
         cudaGetLastError();
@@ -560,6 +754,29 @@ int mcb200_device(const mcb200_ctx *ctx) { return ctx ? ctx->device : -1; }
 int mcb200_sm_count(const mcb200_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t mcb200_launch_count(const mcb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 const char *mcb200_last_error(const mcb200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int mcb200_set_option(mcb200_ctx *ctx, int option, int value)
+{
+    if (!ctx)
+        return MCB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    switch (option) {
+        case MCB200_OPT_TIMING: ctx->timing = value != 0; return MCB200_OK;
+        case MCB200_OPT_OVERLAP: ctx->overlap = value != 0; return MCB200_OK;
+        default: return MCB200_ERR_INVALID;
+    }
+}
+
+int mcb200_get_option(const mcb200_ctx *ctx, int option)
+{
+    if (!ctx)
+        return -1;
+    switch (option) {
+        case MCB200_OPT_TIMING: return ctx->timing ? 1 : 0;
+        case MCB200_OPT_OVERLAP: return ctx->overlap ? 1 : 0;
+        default: return -1;
+    }
+}
 
 int mcb200_set_basket_engine(int engine)
 {
@@ -588,11 +805,7 @@ int mcb200_peer_create(mcb200_ctx *ctx, int rank, int world, mcb200_peer **out, 
     p->world = world;
     cudaError_t e = cudaMalloc(&p->mailbox, kPeerMailboxBytes);
     if (e == cudaSuccess)
-        e = cudaMalloc(&p->ticket, sizeof(unsigned int));
-    if (e == cudaSuccess)
         e = cudaMemset(p->mailbox, 0, kPeerMailboxBytes);
-    if (e == cudaSuccess)
-        e = cudaMemset(p->ticket, 0, sizeof(unsigned int));
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess)
         e = cudaIpcGetMemHandle(&h, p->mailbox);
@@ -600,10 +813,12 @@ int mcb200_peer_create(mcb200_ctx *ctx, int rank, int world, mcb200_peer **out, 
         e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         if (p->mailbox) cudaFree(p->mailbox);
-        if (p->ticket) cudaFree(p->ticket);
         delete p;
         return fail_cuda(ctx, e, "mcb200_peer_create");
     }
+    const char *env = std::getenv("MCB200_PEER_TIMEOUT_MS");
+    if (env && std::atof(env) > 0)
+        p->timeout_ns = (unsigned long long)(std::atof(env) * 1e6);
     std::memcpy(handle, &h, sizeof h);
     p->mail[rank] = p->mailbox;
     *out = p;
@@ -674,6 +889,41 @@ int mcb200_peer_attach(mcb200_ctx *ctx, mcb200_peer *peer)
     return MCB200_OK;
 }
 
+int mcb200_peer_set_mode(mcb200_peer *p, int mode)
+{
+    if (!p || (mode != MCB200_PEER_WAIT && mode != MCB200_PEER_PUSH))
+        return MCB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(p->ctx->mu);
+    p->mode = mode == MCB200_PEER_PUSH ? kPeerPush : kPeerWait;
+    return MCB200_OK;
+}
+
+int mcb200_peer_set_timeout_ms(mcb200_peer *p, double ms)
+{
+    if (!p || !(ms > 0))
+        return MCB200_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(p->ctx->mu);
+    p->timeout_ns = (unsigned long long)(ms * 1e6);
+    return MCB200_OK;
+}
+
+int mcb200_peer_pull(mcb200_peer *p, uint64_t *d_acc, void *stream)
+{
+    if (!p || !d_acc || !p->connected)
+        return MCB200_ERR_INVALID;
+    mcb200_ctx *ctx = p->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (p->seq == 0)
+        return fail(ctx, MCB200_ERR_INVALID, "mcb200_peer_pull before the group's first launch");
+    DeviceGuard guard(ctx->device);
+    MCB_CUDA(ctx, guard.status());
+    peer_pull_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(p->mailbox, p->world, p->seq, p->timeout_ns,
+                                                              (unsigned long long *)d_acc);
+    MCB_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return MCB200_OK;
+}
+
 int mcb200_peer_destroy(mcb200_peer *p)
 {
     if (!p)
@@ -689,7 +939,6 @@ int mcb200_peer_destroy(mcb200_peer *p)
             if (p->opened[r])
                 cudaIpcCloseMemHandle(p->mail[r]);
         if (p->mailbox) cudaFree(p->mailbox);
-        if (p->ticket) cudaFree(p->ticket);
         cudaGetLastError();
     }
     delete p;
@@ -706,6 +955,7 @@ const char *mcb200_strerror(int status)
         case MCB200_ERR_OVERFLOW: return "partial sum outside the fixed-point window, or NaN";
         case MCB200_ERR_UNSUPPORTED: return "unsupported size";
         case MCB200_ERR_ALIGNMENT: return "range not aligned to the job's chunk / draw-unit grid";
+        case MCB200_ERR_PEER_TIMEOUT: return "a peer rank did not deliver its partial sums in time (or the pull came too late)";
         default: return "unknown status";
     }
 }
@@ -784,6 +1034,8 @@ int mcb200_finalize(const mcb200_plan_t *plan, const uint64_t acc[MCB200_ACC_WOR
     const long double sd = sqrtl(var);
     out->confidence = (double)(1.96L * sd / sqrtl(n));
     out->std_error = (double)((long double)plan->discount * sd / sqrtl(n));
+    if ((acc[11] >> 32) != 0)
+        return MCB200_ERR_PEER_TIMEOUT;  // a fused launch gave up waiting for a peer: no rank may trust these totals
     if (acc[11] != 0)
         return MCB200_ERR_OVERFLOW;
     if (acc[10] != plan->total_paths)
@@ -807,8 +1059,10 @@ int mcb200_vanilla_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb2
     std::lock_guard<std::mutex> lock(ctx->mu);
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
-    return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
-                   (cudaStream_t)stream, /*fused=*/true);
+    Sink sink;
+    sink.d_acc = (unsigned long long *)d_acc;
+    sink.fused = true;
+    return enqueue(ctx, *plan, job, first_chunk, n_chunks, sink, (cudaStream_t)stream);
 }
 
 int mcb200_basket_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_basket_t *opt, uint64_t seed,
@@ -826,8 +1080,10 @@ int mcb200_basket_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb20
     std::lock_guard<std::mutex> lock(ctx->mu);
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
-    return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
-                   (cudaStream_t)stream, /*fused=*/true);
+    Sink sink;
+    sink.d_acc = (unsigned long long *)d_acc;
+    sink.fused = true;
+    return enqueue(ctx, *plan, job, first_chunk, n_chunks, sink, (cudaStream_t)stream);
 }
 
 int mcb200_cva_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_cva_t *cva, uint64_t seed,
@@ -845,8 +1101,10 @@ int mcb200_cva_launch(mcb200_ctx *ctx, const mcb200_plan_t *plan, const mcb200_c
     std::lock_guard<std::mutex> lock(ctx->mu);
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
-    return enqueue(ctx, *plan, job, first_chunk, n_chunks, (unsigned long long *)d_acc,
-                   (cudaStream_t)stream, /*fused=*/true);
+    Sink sink;
+    sink.d_acc = (unsigned long long *)d_acc;
+    sink.fused = true;
+    return enqueue(ctx, *plan, job, first_chunk, n_chunks, sink, (cudaStream_t)stream);
 }
 
 // ---- one-call pricing ----
@@ -910,75 +1168,173 @@ int mcb200_cva(mcb200_ctx *ctx, int precision, const mcb200_cva_t *cva, uint64_t
     return mcb200_cva_multi(&ctx, 1, precision, cva, n_paths, seed, out);
 }
 
-// ---- batched pricing: many jobs, one synchronisation ----
+// ---- batched pricing: many jobs, few launches, one wait ----
 // The reference's cvaOpt driver prices 5 grids x 4 thread counts one blocking call at a time, each
 // with its own allocations, XORWOW seeding and device-to-host copy (double_precision/cvaOpt.cu:70-109).
-// Here every job is enqueued on the context's stream into its own accumulator block, and the host
-// waits and reads back ONCE; a job's result is exactly what the one-call API returns for it.
+// Here the European-call and CVA jobs of a batch that share a kernel (workload, precision) go out as ONE launch of
+// the multi-job kernel (device_common.cuh, mc_accumulate_batch_kernel; up to kBatchMaxJobs jobs and, for the CVA,
+// kCvaMaxDates exposure dates per launch), basket jobs as one launch each (their factor lives at fixed offsets of
+// a __constant__ table); every launch overlaps the tail of the one before it, every job's result lands in its own
+// slot of mapped host memory, and the host waits once.  A job's result is exactly what the one-call API returns
+// for it (same chunks, same integer limbs).
 int mcb200_price_batch(mcb200_ctx *ctx, int n_jobs, const mcb200_job_t *jobs, mcb200_result_t *out, int *status_out)
 {
-    if (!ctx || n_jobs < 1 || !jobs || !out)
+    if (!ctx || n_jobs < 1 || n_jobs > 65535 || !jobs || !out)
         return MCB200_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     DeviceGuard guard(ctx->device);
     MCB_CUDA(ctx, guard.status());
     if ((size_t)n_jobs > ctx->batch_capacity) {
-        if (ctx->d_batch)
-            cudaFree(ctx->d_batch);
-        if (ctx->h_batch)
-            cudaFreeHost(ctx->h_batch);
-        ctx->d_batch = ctx->h_batch = nullptr;
+        if (ctx->h_batch_slots) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFreeHost(ctx->h_batch_slots);
+        }
+        ctx->h_batch_slots = ctx->d_batch_slots = nullptr;
         ctx->batch_capacity = 0;
-        const size_t bytes = sizeof(unsigned long long) * kAccWords * (size_t)n_jobs;
-        MCB_CUDA(ctx, cudaMalloc(&ctx->d_batch, bytes));
-        MCB_CUDA(ctx, cudaMallocHost(&ctx->h_batch, bytes));
+        const size_t bytes = sizeof(unsigned long long) * kPeerSlotWords * (size_t)n_jobs;
+        MCB_CUDA(ctx, cudaHostAlloc(&ctx->h_batch_slots, bytes, cudaHostAllocMapped));
+        MCB_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_batch_slots, ctx->h_batch_slots, 0));
+        std::memset(ctx->h_batch_slots, 0, bytes);
         ctx->batch_capacity = (size_t)n_jobs;
     }
-    const size_t bytes = sizeof(unsigned long long) * kAccWords * (size_t)n_jobs;
     std::vector<mcb200_plan_t> plans((size_t)n_jobs);
+    std::vector<AnyJob> built((size_t)n_jobs);
     std::vector<int> status((size_t)n_jobs, MCB200_OK);
-    MCB_CUDA(ctx, cudaMemsetAsync(ctx->d_batch, 0, bytes, ctx->stream));
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
     for (int i = 0; i < n_jobs; i++) {
         const mcb200_job_t &j = jobs[i];
-        AnyJob job;
         int st = MCB200_ERR_INVALID;
         if (j.params) {
             switch (j.workload) {
                 case MCB200_VANILLA:
                     st = mcb200_plan_vanilla(j.precision, (const mcb200_option_t *)j.params, j.n_paths, &plans[i]);
                     if (st == MCB200_OK)
-                        st = make_vanilla_job(j.precision, (const mcb200_option_t *)j.params, j.seed, &job.vanilla);
+                        st = make_vanilla_job(j.precision, (const mcb200_option_t *)j.params, j.seed, &built[i].vanilla);
                     break;
                 case MCB200_BASKET:
                     st = mcb200_plan_basket(j.precision, (const mcb200_basket_t *)j.params, j.n_paths, &plans[i]);
                     if (st == MCB200_OK)
-                        st = make_basket_job((const mcb200_basket_t *)j.params, j.seed, &job.basket);
+                        st = make_basket_job((const mcb200_basket_t *)j.params, j.seed, &built[i].basket);
                     break;
                 case MCB200_CVA:
                     st = mcb200_plan_cva(j.precision, (const mcb200_cva_t *)j.params, j.n_paths, &plans[i]);
                     if (st == MCB200_OK)
-                        st = make_cva_job(j.precision, (const mcb200_cva_t *)j.params, j.seed, &job.cva);
+                        st = make_cva_job(j.precision, (const mcb200_cva_t *)j.params, j.seed, &built[i].cva);
                     break;
                 default: break;
             }
         }
-        if (st == MCB200_OK)
-            st = enqueue(ctx, plans[i], job, 0, plans[i].n_chunks, ctx->d_batch + (size_t)i * kAccWords, ctx->stream);
+        if (st == MCB200_OK && plans[i].n_chunks > (1ull << 30))
+            st = MCB200_ERR_UNSUPPORTED;
         status[i] = st;
     }
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
-    MCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_batch, ctx->d_batch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    order_streams(ctx, ctx->stream);
+    const unsigned long long flag = peer_flag(++ctx->results);
+    if (ctx->timing)
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+    // consecutive launches of the batch are independent: let each start while its predecessor drains (one in
+    // kCtlRing stays a full stream dependency, so the ring of control blocks can never be lapped)
+    auto options = [&]() {
+        LaunchOptions opt;
+        opt.overlap = (ctx->launches % kCtlRing) != 0;
+        return opt;
+    };
+    // ---- multi-job launches: European calls and CVAs grouped by kernel ----
+    std::vector<char> done((size_t)n_jobs, 0);
+    for (int workload : {MCB200_VANILLA, MCB200_CVA}) {
+        for (int precision : {MCB200_F32, MCB200_F64}) {
+            std::vector<int> members;
+            for (int i = 0; i < n_jobs; i++)
+                if (status[i] == MCB200_OK && jobs[i].workload == workload && jobs[i].precision == precision)
+                    members.push_back(i);
+            if (members.size() < 2)
+                continue;  // a lone job takes the one-job kernel below (its parameters sit in the constant bank)
+            // heaviest chunks first: what is claimed last is then the cheapest
+            auto chunk_cost = [&](int i) {
+                return (double)plans[i].rounds * (workload == MCB200_CVA ? (double)std::max(built[i].cva.job.n_dates, 1) : 1.0);
+            };
+            std::stable_sort(members.begin(), members.end(), [&](int a, int b) { return chunk_cost(a) > chunk_cost(b); });
+            size_t at = 0;
+            while (at < members.size()) {
+                BatchShape shape{};
+                std::vector<VanillaJob> vjobs;
+                std::vector<CvaJob> cjobs;
+                uint64_t chunks = 0;
+                int dates = 0;
+                while (at < members.size() && shape.n_jobs < kBatchMaxJobs) {
+                    const int i = members[at];
+                    const int nd = workload == MCB200_CVA ? built[i].cva.job.n_dates : 0;
+                    if (shape.n_jobs > 0 && (chunks + plans[i].n_chunks > (1ull << 30) || dates + nd > kCvaMaxDates))
+                        break;
+                    shape.geo[shape.n_jobs] = job_geometry(plans[i]);
+                    shape.n_chunks[shape.n_jobs] = (unsigned int)plans[i].n_chunks;
+                    shape.slot[shape.n_jobs] = (unsigned short)i;
+                    shape.n_jobs++;
+                    chunks += plans[i].n_chunks;
+                    dates += nd;
+                    if (workload == MCB200_CVA)
+                        cjobs.push_back(built[i].cva.job);
+                    else
+                        vjobs.push_back(built[i].vanilla);
+                    at++;
+                }
+                const int per_sm = workload == MCB200_CVA ? cva_batch_blocks_per_sm(precision) : vanilla_batch_blocks_per_sm(precision);
+                uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)std::max(per_sm, 0);
+                if (grid > chunks)
+                    grid = chunks;
+                cudaError_t e = cudaErrorLaunchOutOfResources;
+                if (grid > 0) {
+                    const int ring = (int)(ctx->launches % kCtlRing);
+                    BatchTarget target;
+                    target.ctl = ctx->d_ctl + ring;
+                    target.d_acc = ctx->d_batch_acc + (size_t)ring * kBatchMaxJobs * kAccWords;
+                    target.host_slots = ctx->d_batch_slots;
+                    target.host_flag = flag;
+                    e = workload == MCB200_CVA
+                            ? cva_batch_launch(precision, shape, cjobs.data(), (int)grid, target, ctx->stream, options())
+                            : vanilla_batch_launch(precision, shape, vjobs.data(), (int)grid, target, ctx->stream, options());
+                }
+                for (int k = 0; k < shape.n_jobs; k++) {
+                    done[shape.slot[k]] = 1;
+                    if (e != cudaSuccess)
+                        status[shape.slot[k]] = fail_cuda(ctx, e, "multi-job kernel launch");
+                }
+                if (e == cudaSuccess)
+                    ctx->launches++;
+            }
+        }
+    }
+    // ---- everything else: one launch per job ----
+    for (int i = 0; i < n_jobs; i++) {
+        if (status[i] != MCB200_OK || done[i])
+            continue;
+        Sink sink;
+        sink.host_slot = ctx->d_batch_slots + (size_t)i * kPeerSlotWords;
+        sink.host_flag = flag;
+        const bool keep = ctx->overlap;
+        ctx->overlap = options().overlap;
+        status[i] = enqueue(ctx, plans[i], built[i], 0, plans[i].n_chunks, sink, ctx->stream);
+        ctx->overlap = keep;
+    }
+    if (ctx->timing)
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
     float ms = 0;
-    MCB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
     int worst = MCB200_OK;
     for (int i = 0; i < n_jobs; i++) {
         std::memset(&out[i], 0, sizeof out[i]);
         if (status[i] == MCB200_OK) {
-            status[i] = mcb200_finalize(&plans[i], (const uint64_t *)(ctx->h_batch + (size_t)i * kAccWords), &out[i]);
-            out[i].kernel_ms = ms;  // device time of the whole batch
+            uint64_t acc[MCB200_ACC_WORDS];
+            status[i] = wait_slot(ctx, ctx->stream, ctx->h_batch_slots + (size_t)i * kPeerSlotWords, flag, acc);
+            if (status[i] == MCB200_OK)
+                status[i] = mcb200_finalize(&plans[i], acc, &out[i]);
         }
+    }
+    if (ctx->timing && (cudaEventSynchronize(ctx->ev_end) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) != cudaSuccess)) {
+        cudaGetLastError();
+        ms = 0;
+    }
+    for (int i = 0; i < n_jobs; i++) {
+        if (status[i] == MCB200_OK)
+            out[i].kernel_ms = ms;  // device time of the whole batch
         if (status_out)
             status_out[i] = status[i];
         if (status[i] != MCB200_OK && worst == MCB200_OK)

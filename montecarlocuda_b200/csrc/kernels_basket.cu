@@ -471,7 +471,7 @@ static void fill_table(const BasketJob &job, BasketTable<Real, N, kFull> &T)
 template <typename Real, int N, bool kFull>
 static cudaError_t launch_t(const BasketJob &job, const Geometry *geom, int grid, unsigned long long *d_acc,
                             unsigned long long first_unit, unsigned long long n_units, void *d_out,
-                            cudaStream_t stream)
+                            cudaStream_t stream, const LaunchOptions &opt)
 {
     using W = Basket<Real, N, kFull>;
     using WA = Basket<Real, N, kFull, true>;
@@ -491,13 +491,20 @@ static cudaError_t launch_t(const BasketJob &job, const Geometry *geom, int grid
             use.invalidate();
             return e;
         }
+        use.uploaded();
     }
+    cudaError_t e;
     if (geom)
-        return accumulate_launch<WA>(grid, pa, *geom, d_acc, stream);
-    const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
-    mc_paths_kernel<W><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(p, first_unit, n_units,
-                                                                                               (Real *)d_out);
-    return cudaGetLastError();
+        e = accumulate_launch<WA>(grid, pa, *geom, d_acc, stream, opt);
+    else {
+        const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
+        mc_paths_kernel<W><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(p, first_unit, n_units,
+                                                                                                   (Real *)d_out);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess)
+        use.invalidate();
+    return e;
 }
 
 template <typename Real, int N, bool kFull>
@@ -540,7 +547,8 @@ static void fill_tc_table(const BasketJob &job, BasketTcTable &T)
 
 template <bool kFull>
 static cudaError_t launch_tc(const BasketJob &job, const Geometry *geom, int grid, unsigned long long *d_acc,
-                             unsigned long long first_unit, unsigned long long n_units, void *d_out, cudaStream_t stream)
+                             unsigned long long first_unit, unsigned long long n_units, void *d_out, cudaStream_t stream,
+                             const LaunchOptions &opt)
 {
     static_assert(sizeof(BasketTcTable) <= kBasketTableBytes, "tensor-core basket table exceeds its constant buffer");
     std::vector<unsigned char> staging(sizeof(BasketTcTable) + 1);
@@ -558,15 +566,20 @@ static cudaError_t launch_tc(const BasketJob &job, const Geometry *geom, int gri
             use.invalidate();
             return e;
         }
+        use.uploaded();
     }
+    cudaError_t e;
     if (geom) {
-        basket_tc_accumulate_kernel<kFull><<<grid, kTcThreads, 0, stream>>>(p, *geom, d_acc);
+        e = launch_kernel(basket_tc_accumulate_kernel<kFull>, grid, kTcThreads, 0, stream, opt.overlap, p, *geom, d_acc);
     } else {
         const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
         basket_tc_paths_kernel<kFull><<<(int)((blocks + 1) / 2 < 148ull ? (blocks + 1) / 2 : 148ull), kTcThreads, 0, stream>>>(p, first_unit, n_units,
                                                                                                        (float *)d_out);
+        e = cudaGetLastError();
     }
-    return cudaGetLastError();
+    if (e != cudaSuccess)
+        use.invalidate();
+    return e;
 }
 
 int basket_padded_width(int n)
@@ -626,14 +639,14 @@ int basket_blocks_per_sm(int precision, int n, bool full)
 }
 
 cudaError_t basket_launch(int precision, const BasketJob &job, const Geometry &geom, int grid,
-                          unsigned long long *d_acc, cudaStream_t stream)
+                          unsigned long long *d_acc, cudaStream_t stream, const LaunchOptions &opt)
 {
     const int n = job.n;
     const bool full = job.full;
     if (basket_uses_tensor_cores(precision, n))
-        return full ? launch_tc<true>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream)
-                    : launch_tc<false>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream);
-#define MCB_LAUNCH(R, W, F) launch_t<R, W, F>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream)
+        return full ? launch_tc<true>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream, opt)
+                    : launch_tc<false>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream, opt);
+#define MCB_LAUNCH(R, W, F) launch_t<R, W, F>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream, opt)
     MCB_BASKET_DISPATCH(MCB_LAUNCH)
 #undef MCB_LAUNCH
     return cudaErrorInvalidValue;
@@ -645,9 +658,9 @@ cudaError_t basket_paths(int precision, const BasketJob &job, unsigned long long
     const int n = job.n;
     const bool full = job.full;
     if (basket_uses_tensor_cores(precision, n))
-        return full ? launch_tc<true>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream)
-                    : launch_tc<false>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream);
-#define MCB_PATHS(R, W, F) launch_t<R, W, F>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream)
+        return full ? launch_tc<true>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream, LaunchOptions())
+                    : launch_tc<false>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream, LaunchOptions());
+#define MCB_PATHS(R, W, F) launch_t<R, W, F>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream, LaunchOptions())
     MCB_BASKET_DISPATCH(MCB_PATHS)
 #undef MCB_PATHS
     return cudaErrorInvalidValue;

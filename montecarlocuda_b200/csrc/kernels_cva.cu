@@ -37,7 +37,6 @@ struct alignas(16) CvaDate {  // three 16-byte constant loads per date
     Real w, inv, c1, sig, kd, pad;
 };
 
-constexpr int kCvaMaxDates = 1024;
 __constant__ __align__(16) unsigned char c_cva_table[kCvaMaxDates * sizeof(CvaDate<double>)];
 static TableLock g_cva_lock;
 
@@ -108,6 +107,7 @@ struct Cva {
         Real y0, mu_dt, k, k_pdf;  // k_pdf = K / sqrt(2 pi)
         PolarScale<Real> scale;  // of sig_dt = v sqrt(dt), folded under the Box-Muller square root
         int n_dates;  // kept dates
+        int first_date;  // of this job in the device table (0 unless the launch carries several jobs)
     };
     // fp64 pricing kernel: replicated tables; math constants from the constant bank only when asked (MCB_CVA_BANK: the
     // right choice under the 80-register cap of 3 sub-blocks, see device_math64.cuh)
@@ -133,7 +133,7 @@ struct Cva {
     static __device__ __forceinline__ void eval(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
                                                 const Shared &sh)
     {
-        const CvaDate<Real> *dates = reinterpret_cast<const CvaDate<Real> *>(c_cva_table);
+        const CvaDate<Real> *dates = reinterpret_cast<const CvaDate<Real> *>(c_cva_table) + P.first_date;
         Real y = P.y0, cva = 0;
         // whole draw blocks run their kNpb dates back to back with no test in between: only y links one date to the
         // next, so the exponentials and reciprocals of neighbouring dates overlap
@@ -176,22 +176,14 @@ static typename W::Params narrow(const CvaJob &job)
     p.k = (Real)job.k;
     p.k_pdf = (Real)(job.k * 0.39894228040143267793994605993438);
     p.n_dates = job.n_dates;
+    p.first_date = 0;
     return p;
 }
 
+// the table image of `n_jobs` jobs laid end to end, uploaded unless the device already holds exactly this image
 template <typename Real>
-static cudaError_t launch_t(const CvaJob &job, const Geometry *geom, int grid, unsigned long long *d_acc,
-                            unsigned long long first_unit, unsigned long long n_units, void *d_out,
-                            cudaStream_t stream)
+static cudaError_t upload_dates(TableUse &use, const std::vector<CvaDate<Real>> &staging, cudaStream_t stream)
 {
-    if (job.n_dates < 0 || job.n_dates > kCvaMaxDates)
-        return cudaErrorInvalidValue;
-    std::vector<CvaDate<Real>> staging((size_t)(job.n_dates > 0 ? job.n_dates : 1));
-    for (int j = 0; j < job.n_dates; j++) {
-        const CvaDateHost &h = job.dates[j];
-        staging[j] = CvaDate<Real>{(Real)h.w, (Real)h.inv, (Real)h.c1, (Real)h.sig, (Real)h.kd, (Real)0};
-    }
-    TableUse use(g_cva_lock, stream, staging.data(), staging.size() * sizeof(CvaDate<Real>));
     if (use.status() != cudaSuccess)
         return use.status();
     if (use.needs_upload()) {
@@ -201,13 +193,87 @@ static cudaError_t launch_t(const CvaJob &job, const Geometry *geom, int grid, u
             use.invalidate();
             return e;
         }
+        use.uploaded();
     }
+    return cudaSuccess;
+}
+template <typename Real>
+static bool stage_dates(const CvaJob &job, std::vector<CvaDate<Real>> &staging)
+{
+    if (job.n_dates < 0 || staging.size() + (size_t)job.n_dates > (size_t)kCvaMaxDates)
+        return false;
+    for (int j = 0; j < job.n_dates; j++) {
+        const CvaDateHost &h = job.dates[j];
+        staging.push_back(CvaDate<Real>{(Real)h.w, (Real)h.inv, (Real)h.c1, (Real)h.sig, (Real)h.kd, (Real)0});
+    }
+    return true;
+}
+
+template <typename Real>
+static cudaError_t launch_t(const CvaJob &job, const Geometry *geom, int grid, unsigned long long *d_acc,
+                            unsigned long long first_unit, unsigned long long n_units, void *d_out,
+                            cudaStream_t stream, const LaunchOptions &opt)
+{
+    std::vector<CvaDate<Real>> staging;
+    if (!stage_dates(job, staging))
+        return cudaErrorInvalidValue;
+    if (staging.empty())
+        staging.push_back(CvaDate<Real>{});
+    TableUse use(g_cva_lock, stream, staging.data(), staging.size() * sizeof(CvaDate<Real>));
+    cudaError_t e = upload_dates(use, staging, stream);
+    if (e != cudaSuccess)
+        return e;
     if (geom)
-        return accumulate_launch<Cva<Real, true>>(grid, narrow<Cva<Real, true>>(job), *geom, d_acc, stream);
-    const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
-    mc_paths_kernel<Cva<Real>><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(
-        narrow<Cva<Real>>(job), first_unit, n_units, (Real *)d_out);
-    return cudaGetLastError();
+        e = accumulate_launch<Cva<Real, true>>(grid, narrow<Cva<Real, true>>(job), *geom, d_acc, stream, opt);
+    else {
+        const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
+        mc_paths_kernel<Cva<Real>><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(
+            narrow<Cva<Real>>(job), first_unit, n_units, (Real *)d_out);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess)
+        use.invalidate();
+    return e;
+}
+
+// many CVA jobs (time grids, options, intensities ...) in one launch: their date tables laid end to end
+template <typename Real>
+static cudaError_t batch_t(const BatchShape &shape, const CvaJob *jobs, int grid, const BatchTarget &target, cudaStream_t stream,
+                           const LaunchOptions &opt)
+{
+    using W = Cva<Real, true>;
+    BatchJobs<W> b{};
+    fill_batch_header(b, shape, target);
+    std::vector<CvaDate<Real>> staging;
+    for (int i = 0; i < shape.n_jobs; i++) {
+        b.params[i] = narrow<W>(jobs[i]);
+        b.params[i].first_date = (int)staging.size();
+        if (!stage_dates(jobs[i], staging))
+            return cudaErrorInvalidValue;
+    }
+    if (staging.empty())
+        staging.push_back(CvaDate<Real>{});
+    TableUse use(g_cva_lock, stream, staging.data(), staging.size() * sizeof(CvaDate<Real>));
+    cudaError_t e = upload_dates(use, staging, stream);
+    if (e != cudaSuccess)
+        return e;
+    e = accumulate_batch_launch<W>(grid, b, stream, opt);
+    if (e != cudaSuccess)
+        use.invalidate();
+    return e;
+}
+
+int cva_batch_blocks_per_sm(int precision)
+{
+    return precision ? accumulate_batch_blocks_per_sm<Cva<double, true>>() : accumulate_batch_blocks_per_sm<Cva<float, true>>();
+}
+
+cudaError_t cva_batch_launch(int precision, const BatchShape &shape, const CvaJob *jobs, int grid, const BatchTarget &target,
+                             cudaStream_t stream, const LaunchOptions &opt)
+{
+    if (shape.n_jobs < 1 || shape.n_jobs > kBatchMaxJobs)
+        return cudaErrorInvalidValue;
+    return precision ? batch_t<double>(shape, jobs, grid, target, stream, opt) : batch_t<float>(shape, jobs, grid, target, stream, opt);
 }
 
 int cva_blocks_per_sm(int precision)
@@ -216,17 +282,17 @@ int cva_blocks_per_sm(int precision)
 }
 
 cudaError_t cva_launch(int precision, const CvaJob &job, const Geometry &geom, int grid,
-                       unsigned long long *d_acc, cudaStream_t stream)
+                       unsigned long long *d_acc, cudaStream_t stream, const LaunchOptions &opt)
 {
-    return precision ? launch_t<double>(job, &geom, grid, d_acc, 0, 0, nullptr, stream)
-                     : launch_t<float>(job, &geom, grid, d_acc, 0, 0, nullptr, stream);
+    return precision ? launch_t<double>(job, &geom, grid, d_acc, 0, 0, nullptr, stream, opt)
+                     : launch_t<float>(job, &geom, grid, d_acc, 0, 0, nullptr, stream, opt);
 }
 
 cudaError_t cva_paths(int precision, const CvaJob &job, unsigned long long first_unit,
                       unsigned long long n_units, void *d_out, cudaStream_t stream)
 {
-    return precision ? launch_t<double>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream)
-                     : launch_t<float>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream);
+    return precision ? launch_t<double>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream, LaunchOptions())
+                     : launch_t<float>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream, LaunchOptions());
 }
 
 }  // namespace mcb

@@ -31,11 +31,37 @@ int vanilla_blocks_per_sm(int precision)
 }
 
 cudaError_t vanilla_launch(int precision, const VanillaJob &job, const Geometry &geom, int grid,
-                           unsigned long long *d_acc, cudaStream_t stream)
+                           unsigned long long *d_acc, cudaStream_t stream, const LaunchOptions &opt)
 {
     if (precision)
-        return accumulate_launch<VanillaAccum<double>>(grid, narrow<VanillaAccum<double>>(job), geom, d_acc, stream);
-    return accumulate_launch<VanillaAccum<float>>(grid, narrow<VanillaAccum<float>>(job), geom, d_acc, stream);
+        return accumulate_launch<VanillaAccum<double>>(grid, narrow<VanillaAccum<double>>(job), geom, d_acc, stream, opt);
+    return accumulate_launch<VanillaAccum<float>>(grid, narrow<VanillaAccum<float>>(job), geom, d_acc, stream, opt);
+}
+
+// many European calls in one launch (mc_accumulate_batch_kernel)
+template <class W>
+static cudaError_t batch_t(const BatchShape &shape, const VanillaJob *jobs, int grid, const BatchTarget &target, cudaStream_t stream,
+                           const LaunchOptions &opt)
+{
+    BatchJobs<W> b{};
+    fill_batch_header(b, shape, target);
+    for (int i = 0; i < shape.n_jobs; i++)
+        b.params[i] = narrow<W>(jobs[i]);
+    return accumulate_batch_launch<W>(grid, b, stream, opt);
+}
+
+int vanilla_batch_blocks_per_sm(int precision)
+{
+    return precision ? accumulate_batch_blocks_per_sm<VanillaAccum<double>>() : accumulate_batch_blocks_per_sm<VanillaAccum<float>>();
+}
+
+cudaError_t vanilla_batch_launch(int precision, const BatchShape &shape, const VanillaJob *jobs, int grid,
+                                 const BatchTarget &target, cudaStream_t stream, const LaunchOptions &opt)
+{
+    if (shape.n_jobs < 1 || shape.n_jobs > kBatchMaxJobs)
+        return cudaErrorInvalidValue;
+    return precision ? batch_t<VanillaAccum<double>>(shape, jobs, grid, target, stream, opt)
+                     : batch_t<VanillaAccum<float>>(shape, jobs, grid, target, stream, opt);
 }
 
 cudaError_t vanilla_paths(int precision, const VanillaJob &job, unsigned long long first_unit,

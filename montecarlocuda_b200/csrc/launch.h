@@ -8,6 +8,38 @@ namespace mcb {
 
 enum : uint32_t { kTagVanilla = 1u, kTagBasket = 2u, kTagCva = 3u };
 
+// ---- many jobs of one kernel in one launch (device_common.cuh: mc_accumulate_batch_kernel) ----
+struct BatchShape {
+    int n_jobs;
+    JobGeometry geo[kBatchMaxJobs];
+    unsigned int n_chunks[kBatchMaxJobs];
+    unsigned short slot[kBatchMaxJobs];   // index of the job's host slot
+};
+struct BatchTarget {
+    LaunchCtl *ctl;
+    unsigned long long *d_acc;         // kBatchMaxJobs x 12 words of zeroed device scratch
+    unsigned long long *host_slots;    // device alias of the mapped host slots
+    unsigned long long host_flag;
+};
+template <class B>
+inline void fill_batch_header(B &b, const BatchShape &shape, const BatchTarget &target)
+{
+    b.n_jobs = shape.n_jobs;
+    b.ctl = target.ctl;
+    b.acc = target.d_acc;
+    b.host_slots = target.host_slots;
+    b.host_flag = target.host_flag;
+    unsigned int first = 0;
+    for (int i = 0; i < shape.n_jobs; i++) {
+        b.first[i] = first;
+        b.geo[i] = shape.geo[i];
+        b.slot[i] = shape.slot[i];
+        first += shape.n_chunks[i];
+    }
+    for (int i = shape.n_jobs; i <= kBatchMaxJobs; i++)
+        b.first[i] = first;
+}
+
 // ---- vanilla (DP/MonteCarloKernel.cu:67-71, :179-220) ----
 // a, b in log2 units for fp32 and natural-log units for fp64 (see kernels_vanilla.cu)
 struct VanillaJob {
@@ -16,7 +48,10 @@ struct VanillaJob {
 };
 int vanilla_blocks_per_sm(int precision);
 cudaError_t vanilla_launch(int precision, const VanillaJob &job, const Geometry &geom, int grid,
-                           unsigned long long *d_acc, cudaStream_t stream);
+                           unsigned long long *d_acc, cudaStream_t stream, const LaunchOptions &opt);
+int vanilla_batch_blocks_per_sm(int precision);
+cudaError_t vanilla_batch_launch(int precision, const BatchShape &shape, const VanillaJob *jobs, int grid,
+                                 const BatchTarget &target, cudaStream_t stream, const LaunchOptions &opt);
 cudaError_t vanilla_paths(int precision, const VanillaJob &job, unsigned long long first_unit,
                           unsigned long long n_units, void *d_out, cudaStream_t stream);
 
@@ -39,11 +74,12 @@ int basket_engine_get();
 void basket_engine_set(int engine);
 bool basket_uses_tensor_cores(int precision, int n);
 cudaError_t basket_launch(int precision, const BasketJob &job, const Geometry &geom, int grid,
-                          unsigned long long *d_acc, cudaStream_t stream);
+                          unsigned long long *d_acc, cudaStream_t stream, const LaunchOptions &opt);
 cudaError_t basket_paths(int precision, const BasketJob &job, unsigned long long first_unit,
                          unsigned long long n_units, void *d_out, cudaStream_t stream);
 
 // ---- CVA (DP/MonteCarloKernel.cu:104-129, :222-283) ----
+constexpr int kCvaMaxDates = 1024;
 struct CvaDateHost {
     double w, inv, c1, sig, kd;
 };
@@ -55,7 +91,11 @@ struct CvaJob {
 };
 int cva_blocks_per_sm(int precision);
 cudaError_t cva_launch(int precision, const CvaJob &job, const Geometry &geom, int grid,
-                       unsigned long long *d_acc, cudaStream_t stream);
+                       unsigned long long *d_acc, cudaStream_t stream, const LaunchOptions &opt);
+// jobs[i].dates are concatenated into the device table (kCvaMaxDates entries in all)
+int cva_batch_blocks_per_sm(int precision);
+cudaError_t cva_batch_launch(int precision, const BatchShape &shape, const CvaJob *jobs, int grid,
+                             const BatchTarget &target, cudaStream_t stream, const LaunchOptions &opt);
 cudaError_t cva_paths(int precision, const CvaJob &job, unsigned long long first_unit,
                       unsigned long long n_units, void *d_out, cudaStream_t stream);
 

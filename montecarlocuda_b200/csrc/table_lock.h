@@ -24,9 +24,11 @@ struct TableLock {
 
 class TableUse {
 public:
-    // `bytes`/`size`: the table image this job needs.  needs_upload() tells the caller whether the
-    // device copy differs.
-    TableUse(TableLock &lock, cudaStream_t stream, const void *bytes, size_t size) : lock_(lock), stream_(stream)
+    // `bytes`/`size`: the table image this job needs.  needs_upload() tells the caller whether the device copy
+    // differs; after the upload has been ENQUEUED successfully the caller says so with uploaded() -- only then does the
+    // cache claim the new image (a failed wait or copy must not leave it describing a table the device never got).
+    TableUse(TableLock &lock, cudaStream_t stream, const void *bytes, size_t size)
+        : lock_(lock), stream_(stream), bytes_((const unsigned char *)bytes), size_(size)
     {
         lock_.mu.lock();
         status_ = cudaGetDevice(&device_);
@@ -34,16 +36,15 @@ public:
             status_ = cudaErrorInvalidDevice;
         if (status_ != cudaSuccess)
             return;
-        std::vector<unsigned char> &res = lock_.resident[device_];
+        const std::vector<unsigned char> &res = lock_.resident[device_];
         upload_ = res.size() != size || std::memcmp(res.data(), bytes, size) != 0;
-        if (upload_)
-            res.assign((const unsigned char *)bytes, (const unsigned char *)bytes + size);
         // always ordered after the table's previous user: its upload may still be in flight on
         // another stream (free when it is the same stream)
         if (lock_.used[device_])
             status_ = cudaStreamWaitEvent(stream_, lock_.last_use[device_], 0);
     }
     bool needs_upload() const { return upload_; }
+    void uploaded() { if (status_ == cudaSuccess) lock_.resident[device_].assign(bytes_, bytes_ + size_); }
     // the upload or launch failed: the device copy is unknown
     void invalidate() { if (device_ >= 0 && device_ < TableLock::kMaxDevices) lock_.resident[device_].clear(); }
     ~TableUse()
@@ -63,6 +64,8 @@ public:
 private:
     TableLock &lock_;
     cudaStream_t stream_;
+    const unsigned char *bytes_;
+    size_t size_;
     int device_ = -1;
     cudaError_t status_ = cudaSuccess;
     bool upload_ = true;

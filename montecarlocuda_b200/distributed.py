@@ -4,8 +4,11 @@ The job's chunks are split into contiguous ranges, rank g of G owning chunks
 [n_chunks * g / G, n_chunks * (g + 1) / G).  Each rank launches ONE kernel on its GPU, which leaves
 a 96-byte accumulator of exact integer limbs in device memory.  The limbs of all ranks are added
   * "peer" (default on GPUs): inside that same kernel -- its last CTA pushes the limbs into every peer's
-    mailbox over NVLink (CUDA IPC memory), waits for the peers' and adds them (mcb200_peer_*, include/mcb200.h;
-    csrc/device_common.cuh peer_combine): no separate collective, no extra launch;
+    mailbox over NVLink (CUDA IPC memory; mcb200_peer_*, include/mcb200.h; csrc/device_common.cuh peer_exchange).
+    Split phase by default: the kernel ends after the push, so ranks do not lock-step on the slowest one and
+    back-to-back jobs overlap; the totals of the LAST enqueued job are summed out of the mailbox by one small
+    kernel when result() asks for them.  `peer_mode="wait"` keeps the single-phase variant (the last CTA also
+    waits for its peers and leaves the job's totals in the accumulator: the kernel is the collective);
   * "nccl": by ONE int64 SUM all-reduce enqueued on the same stream as the kernel (also the gloo path of the
     CPU tests).
 Integer addition is associative, so the combined limbs -- and therefore price and standard error -- are
@@ -74,6 +77,14 @@ class PeerGroup:
     def detach(self):
         _lib.check(self.engine._lib.mcb200_peer_attach(self.engine.handle, None), self.engine.handle)
 
+    def set_mode(self, mode: str):
+        code = {"wait": _lib.PEER_WAIT, "push": _lib.PEER_PUSH}[mode]
+        _lib.check(self.engine._lib.mcb200_peer_set_mode(self._peer, code), self.engine.handle)
+
+    def pull(self, acc, stream: int):
+        """Enqueue the second phase of the most recent push-mode launch: job totals -> acc (12 int64 on the device)."""
+        _lib.check(self.engine._lib.mcb200_peer_pull(self._peer, C.c_void_p(acc.data_ptr()), C.c_void_p(stream)), self.engine.handle)
+
     def close(self):
         if self._peer:
             self.engine._lib.mcb200_peer_destroy(self._peer)
@@ -93,13 +104,15 @@ def _exchange_over_process_group(group):
 
 class ShardedPricer:
     """One rank's view of a sharded pricing job: persistent engine + device accumulator.
-    combine = "peer": the cross-GPU sum runs inside the pricing kernel over peer memory; "nccl": one all-reduce
-    after it; "auto": peer when the group has more than one rank, falling back to nccl (with the reason kept in
-    `combine_note`) only if the peer mailboxes cannot be mapped."""
+    combine = "peer": the cross-GPU sum runs inside the pricing kernel over peer memory (peer_mode "push": split phase,
+    "wait": single phase); "nccl": one all-reduce after it; "auto": peer when the group has more than one rank,
+    falling back to nccl (with the reason kept in `combine_note`) only if the peer mailboxes cannot be mapped.
+    overlap: launch with programmatic dependent launch, so that back-to-back jobs overlap tail and start."""
 
     RING = 32
 
-    def __init__(self, engine: Engine | None = None, device: int | None = None, group=None, combine: str = "auto"):
+    def __init__(self, engine: Engine | None = None, device: int | None = None, group=None, combine: str = "auto",
+                 peer_mode: str = "push", overlap: bool = True):
         import torch
 
         if device is None:
@@ -107,6 +120,7 @@ class ShardedPricer:
         self.torch = torch
         self.device = torch.device("cuda", device)
         self.engine = engine or Engine(device)
+        self.engine.set_overlap(overlap)
         self.group = group
         # a ring of accumulator blocks zeroed in one memset every RING steps (no memset kernel per step)
         self.ring = torch.zeros((self.RING, _lib.ACC_WORDS), dtype=torch.int64, device=self.device)
@@ -115,11 +129,15 @@ class ShardedPricer:
         self.host = torch.zeros(_lib.ACC_WORDS, dtype=torch.int64).pin_memory()
         self._job_key = None
         self._job = None
+        self._pulled = True
         self.peers = None
         self.combine_note = ""
         rank, world = self._world()
         if combine not in ("auto", "peer", "nccl"):
             raise ValueError("combine must be 'auto', 'peer' or 'nccl'")
+        if peer_mode not in ("push", "wait"):
+            raise ValueError("peer_mode must be 'push' or 'wait'")
+        self.peer_mode = peer_mode
         self.combine = "nccl"
         if world > 1 and combine in ("auto", "peer"):
             import torch.distributed as dist
@@ -127,6 +145,7 @@ class ShardedPricer:
             try:
                 with torch.cuda.device(self.device):
                     self.peers = PeerGroup(self.engine, rank, world, _exchange_over_process_group(self.group))
+                    self.peers.set_mode(peer_mode)
                 self.combine = "peer"
             except Exception as exc:  # mapping peer memory can be refused by the platform (IPC disabled, no P2P)
                 failure = exc
@@ -151,17 +170,18 @@ class ShardedPricer:
         return 0, 1
 
     def enqueue(self, workload: str, params, n_paths: int, precision=_lib.F64, seed: int = DEFAULT_SEED):
-        """Asynchronously: zero the accumulator, run this rank's shard, all-reduce.  Returns the plan."""
+        """Asynchronously: run this rank's shard and start the combine.  Returns the plan."""
         torch = self.torch
-        key = (workload, id(params), n_paths, precision, seed)
+        # keyed by VALUE: the parameter dataclasses are mutable, `opt.k = k; pricer.price(...)` must price the new strike
+        key = (workload, params._snapshot(), n_paths, precision, seed)
         if key != self._job_key:        # plan, shard range and C structs of a repeated job are built once
             rank, world = self._world()
             p = plan(workload, params, n_paths, precision)
             first, count = shard_range(p, rank, world)
             lib = self.engine._lib
             fn = {"vanilla": lib.mcb200_vanilla_launch, "basket": lib.mcb200_basket_launch, "cva": lib.mcb200_cva_launch}[workload]
-            self._job_key, self._job = key, (p, first, count, fn, params._c(), params)
-        p, first, count, fn, c_params, _ = self._job
+            self._job_key, self._job = key, (p, first, count, fn, params._c())   # the struct owns its buffers
+        p, first, count, fn, c_params = self._job
         with torch.cuda.device(self.device):
             self.slot = (self.slot + 1) % self.RING
             if self.slot == 0:
@@ -170,14 +190,20 @@ class ShardedPricer:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             _lib.check(fn(self.engine.handle, C.byref(p), C.byref(c_params), seed, first, count,
                           C.c_void_p(self.acc.data_ptr()), C.c_void_p(stream)), self.engine.handle)
-            if self.combine != "peer":   # "peer": the kernel itself left the job's totals in acc
+            if self.combine != "peer":   # "peer": the kernel itself pushed (and, in wait mode, summed) the limbs
                 combine_accumulators(self.acc, self.group)
+            self._pulled = not (self.combine == "peer" and self.peer_mode == "push")
         return p
 
     def result(self, p: _lib.PlanT) -> OptionValue:
-        """Device -> host copy of the combined accumulator and the closing formulas."""
-        self.host.copy_(self.acc, non_blocking=True)
-        self.torch.cuda.current_stream(self.device).synchronize()
+        """The combined accumulator of the LAST enqueued job: [second phase of the combine ->] device -> host copy ->
+        closing formulas."""
+        with self.torch.cuda.device(self.device):
+            if not self._pulled:
+                self.peers.pull(self.acc, self.torch.cuda.current_stream(self.device).cuda_stream)
+                self._pulled = True
+            self.host.copy_(self.acc, non_blocking=True)
+            self.torch.cuda.current_stream(self.device).synchronize()
         return finalize(p, self.host.numpy().view(np.uint64))
 
     def price(self, workload: str, params, n_paths: int, precision=_lib.F64, seed: int = DEFAULT_SEED) -> OptionValue:

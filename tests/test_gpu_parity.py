@@ -422,17 +422,3 @@ def test_linearity_in_notional(engine):
     a = engine.vanilla(VAN, 1 << 20, "f64", 9)
     b = engine.vanilla(m.OptionData(200.0, 200.0, 0.05, 0.2, 1.0), 1 << 20, "f64", 9)
     assert b.sum == pytest.approx(2 * a.sum, rel=1e-13) and b.sumsq == pytest.approx(4 * a.sumsq, rel=1e-13)
-
-
-def test_batched_sweep_matches_single_calls(engine, oracle):
-    """mcb200_price_batch: the reference cvaOpt sweep {25, 50, 75, 250, 500} dates plus a
-    vanilla and a basket job, one synchronisation; every result is bit-identical to its one-call price."""
-    jobs = [("cva", m.CVA(0.03, 0.6, m.OptionData(100.0, 100.0, 0.05, 0.2, 1.0), n), 131072, "f64") for n in (25, 50, 75, 250, 500)]
-    jobs += [("cva", m.CVA(0.03, 0.6, m.OptionData(100.0, 100.0, 0.05, 0.2, 1.0), 50), 131072, "f32"),
-             ("vanilla", VAN, 1 << 20, "f64"), ("vanilla", VAN, (1 << 20) + 3, "f32"), ("basket", make_basket(oracle, 10), 1 << 18, "f64")]
-    batch = engine.price_batch(jobs)
-    for (workload, params, n_paths, prec), got in zip(jobs, batch):
-        one = getattr(engine, workload)(params, n_paths, prec)
-        assert (got.Expected, got.Confidence, got.sum, got.sumsq, got.n_paths) == (one.Expected, one.Confidence, one.sum, one.sumsq, one.n_paths)
-    with pytest.raises(m.Mcb200Error):
-        engine.price_batch([("vanilla", VAN, 0, "f64")])

@@ -95,6 +95,8 @@ def test_serialised_ranks_raise_the_error_flag(engine):
     from montecarlocuda_b200 import distributed as D
     group = LocalGroup(2)
     try:
+        for peer in group.peers:   # the wait is bounded by wall clock (default 10 s): keep the test short
+            _lib.check(group.lib.mcb200_peer_set_timeout_ms(peer, 300.0))
         p = m.plan("vanilla", VAN, 1 << 16, "f64")
         acc = torch.zeros((2, 12), dtype=torch.int64, device="cuda:0")
         stream = torch.cuda.Stream()
@@ -103,9 +105,10 @@ def test_serialised_ranks_raise_the_error_flag(engine):
             D._launch(group.engines[rank], "vanilla", p, VAN, 3, first, count, acc[rank], stream.cuda_stream)
         torch.cuda.synchronize()
         a = acc.cpu().numpy().view(np.uint64)
-        assert a[0][11] >= 1                       # rank 0 gave up waiting
-        with pytest.raises(m.Mcb200Error):
+        assert a[0][11] >> 32 >= 1                 # rank 0 gave up waiting: the peer-timeout flag, not the overflow count
+        with pytest.raises(m.Mcb200Error) as err:
             m.finalize(p, a[0])
+        assert err.value.status == _lib.ERR_PEER_TIMEOUT
         assert a[1][11] == 0 and a[1][10] == 1 << 16   # rank 1 found rank 0's words already there
     finally:
         group.close()
@@ -122,5 +125,71 @@ def test_detached_context_launches_are_plain_shards(engine):
         total = acc.sum(axis=0)
         one = engine.vanilla(VAN, 1 << 20, "f64", 9)
         assert m.finalize(p, total).sum == one.sum
+    finally:
+        group.close()
+
+
+# ---- split phase (MCB200_PEER_PUSH + mcb200_peer_pull) ------------------------------------------------
+def _push_then_pull(group, workload, params, n_paths, prec, seed, stream):
+    """Every virtual rank launches its shard on ONE stream (a push never waits, so they may run one after the other),
+    then every rank pulls the totals of that launch out of its own mailbox."""
+    import torch
+    from montecarlocuda_b200 import distributed as D
+    world = len(group.engines)
+    p = m.plan(workload, params, n_paths, prec)
+    acc = torch.full((world, 12), -1, dtype=torch.int64, device="cuda:0")   # poisoned: the pull overwrites all 12 words
+    for rank in range(world):
+        first, count = m.shard_range(p, rank, world)
+        D._launch(group.engines[rank], workload, p, params, seed, first, count, acc[rank], stream.cuda_stream)
+    for rank in range(world):
+        _lib.check(group.lib.mcb200_peer_pull(group.peers[rank], C.c_void_p(acc[rank].data_ptr()), C.c_void_p(stream.cuda_stream)))
+    torch.cuda.synchronize()
+    return p, acc.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("world", [2, 5, 8])
+def test_split_phase_combine(engine, oracle, world):
+    import torch
+    from test_gpu_parity import CVA50, make_basket
+    group = LocalGroup(world)
+    try:
+        for peer in group.peers:
+            _lib.check(group.lib.mcb200_peer_set_mode(peer, _lib.PEER_PUSH))
+        stream = torch.cuda.Stream()
+        # basket and CVA can take part now: nobody waits inside a kernel, so sharing the device's table is no deadlock
+        cases = [("vanilla", VAN, (1 << 22) + 12345, "f32"), ("vanilla", VAN, 1000, "f64"), ("cva", CVA50, 50_000, "f64"),
+                 ("basket", make_basket(oracle, 10), 30_000, "f64")]
+        for workload, params, n_paths, prec in cases:
+            for _ in range(5):   # more launches than the mailbox ring is deep on small worlds: slots are reused
+                p, acc = _push_then_pull(group, workload, params, n_paths, prec, 2024, stream)
+                for rank in range(1, world):
+                    assert np.array_equal(acc[rank], acc[0]), (workload, prec, rank)
+                assert acc[0][10] == n_paths and acc[0][11] == 0
+            one = getattr(engine, workload)(params, n_paths, prec, 2024)
+            fin = m.finalize(p, acc[0])
+            assert (one.Expected, one.Confidence, one.sum, one.sumsq) == (fin.Expected, fin.Confidence, fin.sum, fin.sumsq)
+    finally:
+        group.close()
+
+
+def test_split_phase_pull_of_a_missing_peer_times_out(engine):
+    """Only rank 0 launches: its pull must end (bounded by the wall-clock timeout) in the peer-timeout status."""
+    import torch
+    from montecarlocuda_b200 import distributed as D
+    group = LocalGroup(2)
+    try:
+        for peer in group.peers:
+            _lib.check(group.lib.mcb200_peer_set_mode(peer, _lib.PEER_PUSH))
+            _lib.check(group.lib.mcb200_peer_set_timeout_ms(peer, 200.0))
+        p = m.plan("vanilla", VAN, 1 << 16, "f64")
+        acc = torch.zeros(12, dtype=torch.int64, device="cuda:0")
+        stream = torch.cuda.Stream()
+        first, count = m.shard_range(p, 0, 2)
+        D._launch(group.engines[0], "vanilla", p, VAN, 3, first, count, acc, stream.cuda_stream)
+        _lib.check(group.lib.mcb200_peer_pull(group.peers[0], C.c_void_p(acc.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        torch.cuda.synchronize()
+        with pytest.raises(m.Mcb200Error) as err:
+            m.finalize(p, acc.cpu().numpy().view(np.uint64))
+        assert err.value.status == _lib.ERR_PEER_TIMEOUT
     finally:
         group.close()

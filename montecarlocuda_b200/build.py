@@ -4,14 +4,19 @@ Outputs, all under montecarlocuda_b200/lib/ (git-ignored, shipped to the GPU box
   libmcb200.so                    kernels + engine + extended C ABI (include/mcb200.h)
   libmcb200_{dp,sp}[_nN].so       the reference's dev_* entry points (include/MonteCarlo.h),
                                   one per precision and basket width N in {3, 10, 64}
-  pipe_peaks                      FMA / DFMA / MUFU / integer pipe micro-benchmark (bench evidence)
+  pipe_peaks                      FMA / DFMA / MUFU / integer pipe micro-benchmark (tools/microbench/, bench evidence)
+  libmcb200.manifest.json         sha256 of libmcb200.so, of the sources it was built from and of the SASS of every
+                                  pricing kernel: bench.py ties ncu counters to the library it actually loaded
 
 Run as `python -m montecarlocuda_b200.build` or through `__graft_entry__.build()`.
 """
 from __future__ import annotations
 
 import concurrent.futures as cf
+import hashlib
+import json
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -112,12 +117,93 @@ def build(verbose: bool = False, force: bool = False) -> Path:
                     _run([cc, "-O2", "-std=gnu11", "-Wall", f"-DN={n}"] + define + ["-I", INCLUDE, src, "-o", exe, f"-L{LIB}",
                          f"-l{dropin}", f"-lmcb200_hostapi_{suffix}", "-lmcb200", "-lm", "-Wl,-rpath,$ORIGIN"], verbose)
 
-    peaks_src = CSRC / "pipe_peaks.cu"
+    peaks_src = ROOT / "tools" / "microbench" / "pipe_peaks.cu"
     if peaks_src.exists():
         peaks = LIB / "pipe_peaks"
         if force or _newer(peaks, [peaks_src, Path(__file__)]):
             _run([nvcc, "-O3", "-std=c++17", "-lineinfo"] + ARCH + [peaks_src, "-o", peaks], verbose)
+    manifest = LIB / "libmcb200.manifest.json"
+    if force or _newer(manifest, [core]):
+        write_manifest(core, manifest)
     return core
+
+
+def source_hash() -> str:
+    """sha256 over the sources and flags libmcb200.so is built from (stable across rebuilds of the same tree)."""
+    h = hashlib.sha256()
+    for name in sorted(CUDA_UNITS + HEADERS):
+        h.update(name.encode())
+        h.update((CSRC / name).read_bytes())
+    h.update((INCLUDE / "mcb200.h").read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def file_hash(path: Path) -> str:
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for block in iter(lambda: f.read(1 << 20), b""):
+            h.update(block)
+    return h.hexdigest()
+
+
+def kernel_sass_hashes(library: Path) -> dict:
+    """{demangled kernel name: sha256 of its SASS instruction text} for every pricing kernel in the library."""
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([tool, "-sass", str(library)], capture_output=True, text=True)
+    if out.returncode != 0:
+        return {}
+    filt = shutil.which("cu++filt") or "/usr/local/cuda/bin/cu++filt"
+    hashes, name, h = {}, None, None
+    for line in out.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            if name is not None:
+                hashes[name] = h.hexdigest()
+            name, h = m.group(1), hashlib.sha256()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(.*?)\s*;", line)
+        if m and name is not None:
+            h.update(m.group(1).encode())
+            h.update(b"\n")
+    if name is not None:
+        hashes[name] = h.hexdigest()
+    keep = {k: v for k, v in hashes.items() if "accumulate" in k}
+    try:
+        res = subprocess.run([filt] + list(keep), capture_output=True, text=True)
+        names = res.stdout.splitlines() if res.returncode == 0 else []
+    except OSError:
+        names = []
+    if len(names) == len(keep):
+        return {short_kernel_name(n): v for n, v in zip(names, keep.values())}
+    return keep
+
+
+def short_kernel_name(demangled: str) -> str:
+    """'void mcb::mc_accumulate_kernel<mcb::Vanilla<double, 2, 1, true>>(...)' -> 'mc_accumulate_kernel<Vanilla<double, 2, 1, true>>'
+    (ncu prints bool template arguments as 1 / 0 and the toolchain's demangler as true / false: normalised here)."""
+    name = demangled.strip()
+    if name.startswith("void "):
+        name = name[5:]
+    depth, cut = 0, len(name)
+    for i, ch in enumerate(name):
+        if ch == "<":
+            depth += 1
+        elif ch == ">":
+            depth -= 1
+        elif ch == "(" and depth == 0:
+            cut = i
+            break
+    name = name[:cut].replace("mcb::", "")
+    name = re.sub(r"\((?:int|bool|unsigned int)\)", "", name)
+    name = re.sub(r"\btrue\b", "1", name)
+    name = re.sub(r"\bfalse\b", "0", name)
+    return re.sub(r"\s+", "", name)
+
+
+def write_manifest(library: Path, manifest: Path) -> None:
+    manifest.write_text(json.dumps({"library": library.name, "library_sha256": file_hash(library), "source_sha256": source_hash(),
+                                    "nvcc_flags": NVCC_FLAGS, "kernel_sass_sha256": kernel_sass_hashes(library)}, indent=1) + "\n")
 
 
 def build_oracle(verbose: bool = False) -> None:

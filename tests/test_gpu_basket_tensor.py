@@ -89,6 +89,24 @@ def test_tensor_price_matches_ffma_and_sums_its_paths(tensor_engine, oracle):
     assert part.sumsq == pytest.approx((vals * vals).sum(), rel=2e-6)
 
 
+@pytest.mark.parametrize("n_assets,n_paths,full", [(64, 70_001, False), (64, 1 << 18, False), (48, 33_333, False), (33, 20_000, False), (40, 25_001, True)])
+def test_tensor_accumulator_is_bit_exact_against_the_oracle_restatement(tensor_engine, oracle, n_assets, n_paths, full):
+    """Like every other pricing kernel (test_pricing_kernels_sum_exactly_their_path_kernels_values): the accumulator of the
+    tensor-core kernel equals, bit for bit, the oracle's restatement of the chunk reduction (fp32 runs per thread, fp64
+    butterfly, warps in order, exact limb split) applied to the engine's own per-path values -- whole and ragged chunks,
+    triangular and full factors."""
+    if full:
+        rng = np.random.default_rng(11)
+        opt = m.MultiOptionData(list(rng.uniform(80, 120, n_assets)), list(rng.uniform(0.1, 0.3, n_assets)), rng.uniform(-0.15, 0.15, (n_assets, n_assets)),
+                                list(rng.uniform(-0.02, 0.02, n_assets)), list(np.full(n_assets, 1.0 / n_assets)), 98.0, 0.75, 0.03)
+    else:
+        opt = make_basket(oracle, n_assets, "f32")
+    p, acc = _shard_accumulators(tensor_engine, "basket", opt, n_paths, "f32", 5, 1)
+    vals = tensor_engine.basket_paths(opt, 0, n_paths, "f32", 5)
+    assert vals.dtype == np.float32
+    assert np.array_equal(acc[0], oracle.accumulate(vals, p))
+
+
 @pytest.mark.parametrize("n_paths", [300_001, 1 << 21])
 def test_tensor_virtual_ranks_bit_identical(tensor_engine, oracle, n_paths):
     opt = make_basket(oracle, 64, "f32")

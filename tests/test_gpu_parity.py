@@ -215,6 +215,47 @@ def test_against_reference_gpu_kernels(engine, oracle, precision, capfd):
     capfd.readouterr()  # the reference prints timing lines on every call
 
 
+@pytest.mark.parametrize("precision", ["dp", "sp"])
+def test_wide_basket_against_reference_gpu_kernel(engine, oracle, precision, capfd):
+    """BASELINE config 5's width: the 64-asset basket against the reference's own GPU kernel (N = 64 build) at 2^22
+    simulations, within 3 combined standard errors -- fp32 through the tensor-core engine AND the packed-FMA engine."""
+    prec = {"dp": "f64", "sp": "f32"}[precision]
+    sims = 1 << 22
+    ref = _reference(precision, 64)
+    opt = make_basket(oracle, 64, prec)
+    rb = ref.lib.dev_basketOpt(ref.multi(opt.s, opt.v, opt.p, opt.d, opt.w, opt.k, opt.t, opt.r), 512, 128, sims)
+    capfd.readouterr()
+    ours = [engine.basket(opt, sims, prec)]
+    if prec == "f32":
+        m.set_basket_engine(m.BASKET_FFMA)
+        ours.append(engine.basket(opt, sims, prec))
+        m.set_basket_engine(m.BASKET_TENSOR)
+    for ob in ours:
+        assert abs(ob.Expected - rb.Expected) < 3 * np.hypot(ob.Confidence, rb.Confidence) / 1.96
+
+
+@pytest.mark.parametrize("precision", ["dp", "sp"])
+@pytest.mark.parametrize("n_dates", [25, 75, 250, 500])
+def test_cva_grids_against_reference_gpu_kernel(engine, oracle, precision, n_dates, capfd):
+    """The other grids of the reference's cvaOpt sweep (cvaOpt.cu:70), each with its own keep / drop of the last
+    date (Q3: 1 - n * (1/n) rounds differently per n and per precision): ours against the reference's GPU kernel
+    within 3 combined standard errors, and the kept-date pattern against the oracle's closed form."""
+    prec = {"dp": "f64", "sp": "f32"}[precision]
+    sims = 1 << 22          # standard error 6.7e-5: the two last-date patterns are 3.8e-4 (n = 500) to 7.7e-3 (n = 25) apart
+    ref = _reference(precision, 3)
+    rc = ref.lib.dev_cvaEquityOption(ref.cva(0.03, 0.6, ref.option(100, 100, 0.05, 0.2, 1.0), n_dates), 1024, 128, sims)
+    capfd.readouterr()
+    oc = engine.cva(m.CVA(0.03, 0.6, m.OptionData(100.0, 100.0, 0.05, 0.2, 1.0), n_dates), sims, prec)
+    assert abs(oc.Expected - rc.Expected) < 3 * np.hypot(oc.Confidence, rc.Confidence) / 1.96
+    _, keep = oracle.cva_grid(1.0, n_dates, prec)
+    kept = oracle.cva_closed_form(100, 100, 0.05, 0.2, 1.0, 0.03, 0.6, n_dates, keep)
+    flipped = oracle.cva_closed_form(100, 100, 0.05, 0.2, 1.0, 0.03, 0.6, n_dates, np.concatenate([keep[:-1], [1 - keep[-1]]]))
+    # the two patterns differ by the last date's weight x its exposure (~ dp_n x intrinsic value): the estimate must side
+    # with the grid's own rounding, and clearly so
+    assert abs(oc.Expected - kept) < 3 * oc.std_error + 2e-5
+    assert abs(oc.Expected - flipped) > abs(oc.Expected - kept)
+
+
 # ------------------------------------------------------------------------------------------------
 # order-free combine: any partition of the chunks gives the same bits
 # ------------------------------------------------------------------------------------------------

@@ -52,6 +52,49 @@ def test_struct_layouts_match_the_reference(ensure_built):
             assert out == want, (flags, out)
 
 
+REFERENCE = Path("/root/reference")
+
+
+@pytest.mark.skipif(not (REFERENCE / "double_precision" / "MonteCarlo.h").exists(), reason="the reference sources are not mounted here")
+@pytest.mark.parametrize("tree,flags", [("double_precision", []), ("single_precision", ["-DMCB200_SINGLE"])])
+@pytest.mark.parametrize("n", [3, 10, 64])
+def test_struct_layouts_against_the_reference_header_itself(ensure_built, tree, flags, n, tmp_path):
+    """Not constants typed in from a survey: the reference's OWN MonteCarlo.h (its `#define N 3` rewritten in a scratch
+    copy for the wider builds, as oracle/Makefile does) and ours are compiled by the same gcc, and every struct's size
+    and every field's offset must agree."""
+    import subprocess
+    probe = r"""
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "MonteCarlo.h"
+    int main(void) {
+        printf("%zu %zu %zu %zu %zu\n", sizeof(OptionData), sizeof(MultiOptionData), sizeof(OptionValue), sizeof(CVA), sizeof(MonteCarloData));
+        printf("%zu %zu %zu %zu %zu\n", offsetof(OptionData, s), offsetof(OptionData, k), offsetof(OptionData, r), offsetof(OptionData, v), offsetof(OptionData, t));
+        printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", offsetof(MultiOptionData, s), offsetof(MultiOptionData, v), offsetof(MultiOptionData, p),
+               offsetof(MultiOptionData, d), offsetof(MultiOptionData, w), offsetof(MultiOptionData, k), offsetof(MultiOptionData, t), offsetof(MultiOptionData, r));
+        printf("%zu %zu\n", offsetof(OptionValue, Expected), offsetof(OptionValue, Confidence));
+        printf("%zu %zu %zu %zu %zu\n", offsetof(CVA, defInt), offsetof(CVA, lgd), offsetof(CVA, ns), offsetof(CVA, option), offsetof(CVA, n));
+        return 0;
+    }
+    """
+    (tmp_path / "probe.c").write_text(probe)
+    ref_dir = tmp_path / "ref"
+    ref_dir.mkdir()
+    header = (REFERENCE / tree / "MonteCarlo.h").read_text()
+    assert "#define N 3" in header
+    # the reference header pulls in the CUDA runtime for its CudaCheck macro; the layouts do not depend on it
+    header = header.replace("#define N 3", f"#define N {n}")
+    header = re.sub(r'#include\s*[<"](cuda[^>"]*|curand[^>"]*|helper[^>"]*)[>"]', "", header)
+    (ref_dir / "MonteCarlo.h").write_text(header)
+    outs = []
+    for include, extra in ((ref_dir, []), (ROOT / "include", flags + [f"-DN={n}"])):
+        exe = tmp_path / f"probe_{len(outs)}"
+        res = subprocess.run(["gcc", "-x", "c", "-I", str(include), *extra, str(tmp_path / "probe.c"), "-o", str(exe)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs.append(subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout)
+    assert outs[0] == outs[1], (tree, n, outs)
+
+
 def test_no_device_fails_loudly(ensure_built):
     import torch
     if torch.cuda.is_available():

@@ -232,8 +232,12 @@ struct ChunkWalk {
     __device__ __forceinline__ bool live(const Geometry &G) const { return chunk < (unsigned int)G.n_chunks; }
     __device__ __forceinline__ void claim_ahead(const Geometry &G, int tid)
     {
+#ifdef MCB_STATIC_STRIDE   // A/B switch (tools/build_variant.sh): the static stride of the first version
+        ahead = chunk + gridDim.x * kSubBlocks;
+#else
         if (tid == 0)
             ahead = gridDim.x * kSubBlocks + atomicAdd(&G.ctl->next, 1u);
+#endif
     }
     __device__ __forceinline__ void advance(const BlockScratch &sc) { chunk = sc.next; }
 };

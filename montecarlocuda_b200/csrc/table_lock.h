@@ -1,7 +1,9 @@
 // table_lock.h -- a __constant__ table is per device and shared by every stream and context of
-// the process, so its users are serialised: the upload of the next job waits (on the device, via
-// an event) for the kernel of the previous one, and the host-side sequence upload -> launch ->
-// record is atomic under a mutex.  The reference has the same hazard (file-scope __constant__
+// the process, so its users are serialised: the host-side sequence upload -> launch is atomic under a mutex, and a
+// user on ANOTHER stream than the previous one first waits (on the host) for that stream, whose kernel may still be
+// reading the table.  Users that follow each other on one stream -- the common case -- are ordered by the stream itself
+// and pay nothing (the first version recorded and waited on an event around every launch: two more stream
+// operations on a 15 us call).  The reference has the same hazard (file-scope __constant__
 // OPTION / MOPTION, DP/MonteCarloKernel.cu:53-59) and no protection.
 #pragma once
 
@@ -15,7 +17,7 @@ namespace mcb {
 struct TableLock {
     static constexpr int kMaxDevices = 64;
     std::mutex mu;
-    cudaEvent_t last_use[kMaxDevices] = {};
+    cudaStream_t last_stream[kMaxDevices] = {};
     bool used[kMaxDevices] = {};
     // what the device's table holds once everything enqueued so far has run: a job repeated with the
     // same parameters skips the upload
@@ -38,10 +40,9 @@ public:
             return;
         const std::vector<unsigned char> &res = lock_.resident[device_];
         upload_ = res.size() != size || std::memcmp(res.data(), bytes, size) != 0;
-        // always ordered after the table's previous user: its upload may still be in flight on
-        // another stream (free when it is the same stream)
-        if (lock_.used[device_])
-            status_ = cudaStreamWaitEvent(stream_, lock_.last_use[device_], 0);
+        // the table's previous user ran on another stream: let it finish (if that stream is gone, so is its work)
+        if (lock_.used[device_] && lock_.last_stream[device_] != stream_ && cudaStreamSynchronize(lock_.last_stream[device_]) != cudaSuccess)
+            cudaGetLastError();
     }
     bool needs_upload() const { return upload_; }
     void uploaded() { if (status_ == cudaSuccess) lock_.resident[device_].assign(bytes_, bytes_ + size_); }
@@ -50,12 +51,8 @@ public:
     ~TableUse()
     {
         if (status_ == cudaSuccess) {
-            if (!lock_.used[device_]) {
-                if (cudaEventCreateWithFlags(&lock_.last_use[device_], cudaEventDisableTiming) == cudaSuccess)
-                    lock_.used[device_] = true;
-            }
-            if (lock_.used[device_])
-                cudaEventRecord(lock_.last_use[device_], stream_);
+            lock_.last_stream[device_] = stream_;
+            lock_.used[device_] = true;
         }
         lock_.mu.unlock();
     }

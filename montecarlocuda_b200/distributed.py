@@ -193,17 +193,23 @@ class ShardedPricer:
             if self.combine != "peer":   # "peer": the kernel itself pushed (and, in wait mode, summed) the limbs
                 combine_accumulators(self.acc, self.group)
             self._pulled = not (self.combine == "peer" and self.peer_mode == "push")
+            self._host_is_current = False
         return p
 
     def result(self, p: _lib.PlanT) -> OptionValue:
         """The combined accumulator of the LAST enqueued job: [second phase of the combine ->] device -> host copy ->
         closing formulas."""
         with self.torch.cuda.device(self.device):
+            stream = self.torch.cuda.current_stream(self.device)
             if not self._pulled:
-                self.peers.pull(self.acc, self.torch.cuda.current_stream(self.device).cuda_stream)
+                # the pull kernel writes the 12 words straight into the pinned host block (unified addressing: the
+                # device reaches pinned memory under the same pointer): no copy operation behind it
+                self.peers.pull(self.host, stream.cuda_stream)
                 self._pulled = True
-            self.host.copy_(self.acc, non_blocking=True)
-            self.torch.cuda.current_stream(self.device).synchronize()
+                self._host_is_current = True
+            elif not getattr(self, "_host_is_current", False):
+                self.host.copy_(self.acc, non_blocking=True)
+            stream.synchronize()
         return finalize(p, self.host.numpy().view(np.uint64))
 
     def price(self, workload: str, params, n_paths: int, precision=_lib.F64, seed: int = DEFAULT_SEED) -> OptionValue:

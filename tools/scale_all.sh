@@ -1,32 +1,36 @@
-# 1/2/4/8-GPU strong-scaling evidence on one box: bench.py under torchrun, every workload, peer-memory combine
-# (plus the NCCL route at 8 GPUs for comparison).  Writes gpurun_out/scale_*.json.
+# 1/2/4/8-GPU strong-scaling evidence on ONE 8-GPU box: bench.py under torchrun, every workload, split-phase peer combine
+# (plus the single-phase variant at 8 GPUs for comparison).  Writes gpurun_out/scale_*.json.
+#   gpurun --gpus 8 --timeout 1500 -- 'bash tools/scale_all.sh'
 set -x
-run() { # n combine tag extra...
-  n=$1; c=$2; tag=$3; shift 3
+run() { # n tag extra...
+  n=$1; tag=$2; shift 2
   if [ "$n" = 1 ]; then
-    timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/scale_$tag.json 2> gpurun_out/scale_$tag.err
+    timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-baseline "$@" > gpurun_out/scale_$tag.json 2> gpurun_out/scale_$tag.err
   else
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) \
-      bench.py --gpus $n --steps 10 --warmup 3 --no-cpu-baseline --combine $c "$@" > gpurun_out/scale_$tag.json 2> gpurun_out/scale_$tag.err
+      bench.py --gpus $n --steps 20 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/scale_$tag.json 2> gpurun_out/scale_$tag.err
   fi
   tail -c 300 gpurun_out/scale_$tag.err | tail -2
 }
-run 8 peer 8
-if [ -z "$QUICK" ]; then  # QUICK=1: only the 8-GPU and the 1-GPU run (8x box time is charged)
-run 8 nccl 8_nccl
-run 4 peer 4
-run 2 peer 2
+run 8 8
+run 8 8_wait --peer-mode wait
+if [ -z "$QUICK" ]; then
+run 4 4
+run 2 2
 fi
-run 1 peer 1
-timeout 900 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/pytest_multi8.log 2>&1; tail -3 gpurun_out/pytest_multi8.log
+run 1 1
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/pytest_multi8.log 2>&1; tail -3 gpurun_out/pytest_multi8.log
 python - <<'PY'
 import json
-for tag in ("1", "2", "4", "8", "8_nccl"):
+rows = {}
+for tag in ("1", "2", "4", "8", "8_wait"):
     try:
         d = json.loads([l for l in open(f"gpurun_out/scale_{tag}.json") if l.startswith("{")][-1])
     except Exception as e:
         print(tag, "FAILED", e); continue
-    print(tag, d["n_gpus"], d["config"]["collective"][:40], "|", d["metric"], "%.4g" % d["value"], "%.3f ms" % d["ms_per_step"], d["price"])
-    for k, v in d["also"].items():
-        print("    ", k, "%.4g" % v["value"], "%.3f ms" % v["ms_per_step"], v["price"])
+    rows[tag] = {d["config"]["workload"]: (d["ms_per_step"], d["limbs"], d["e2e"]["ms_per_call"]), **{k: (v["ms_per_step"], v.get("limbs"), v.get("e2e_ms")) for k, v in d["also"].items() if "ms_per_step" in v}}
+for w in rows.get("1", {}):
+    t1 = rows["1"][w][0]
+    print(f"{w:20s} 1 GPU {t1:9.4f} ms |", "  ".join(f"{tag}: {rows[tag][w][0]:8.4f} ms x{t1 / rows[tag][w][0]:.3f} (e2e {rows[tag][w][2]:.4f})" for tag in rows if tag != "1" and w in rows[tag]),
+          "| bits", "same" if all(rows[tag][w][1] == rows["1"][w][1] for tag in rows if w in rows[tag]) else "DIFFER")
 PY

@@ -127,6 +127,7 @@ class ShardedPricer:
         self.slot = 0
         self.acc = self.ring[0]
         self.host = torch.zeros(_lib.ACC_WORDS, dtype=torch.int64).pin_memory()
+        self._host_words = self.host.numpy().view(np.uint64)
         self._job_key = None
         self._job = None
         self._pulled = True
@@ -182,35 +183,40 @@ class ShardedPricer:
             fn = {"vanilla": lib.mcb200_vanilla_launch, "basket": lib.mcb200_basket_launch, "cva": lib.mcb200_cva_launch}[workload]
             self._job_key, self._job = key, (p, first, count, fn, params._c())   # the struct owns its buffers
         p, first, count, fn, c_params = self._job
-        with torch.cuda.device(self.device):
+        # (no torch.cuda.device() around this: the library selects its context's device itself, and the stream is asked
+        # for by device -- the context manager alone was 10 us of a 15 us launch)
+        push = self.combine == "peer" and self.peer_mode == "push"
+        if not push:                     # the launch ADDS to the block: a zeroed one (push mode never touches it)
             self.slot = (self.slot + 1) % self.RING
             if self.slot == 0:
-                self.ring.zero_()
+                with torch.cuda.device(self.device):
+                    self.ring.zero_()
             self.acc = self.ring[self.slot]
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(fn(self.engine.handle, C.byref(p), C.byref(c_params), seed, first, count,
-                          C.c_void_p(self.acc.data_ptr()), C.c_void_p(stream)), self.engine.handle)
-            if self.combine != "peer":   # "peer": the kernel itself pushed (and, in wait mode, summed) the limbs
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(fn(self.engine.handle, C.byref(p), C.byref(c_params), seed, first, count,
+                      C.c_void_p(self.acc.data_ptr()), C.c_void_p(stream)), self.engine.handle)
+        if self.combine != "peer":       # "peer": the kernel itself pushed (and, in wait mode, summed) the limbs
+            with torch.cuda.device(self.device):
                 combine_accumulators(self.acc, self.group)
-            self._pulled = not (self.combine == "peer" and self.peer_mode == "push")
-            self._host_is_current = False
+        self._pulled = not push
+        self._host_is_current = False
         return p
 
     def result(self, p: _lib.PlanT) -> OptionValue:
         """The combined accumulator of the LAST enqueued job: [second phase of the combine ->] device -> host copy ->
         closing formulas."""
-        with self.torch.cuda.device(self.device):
-            stream = self.torch.cuda.current_stream(self.device)
-            if not self._pulled:
-                # the pull kernel writes the 12 words straight into the pinned host block (unified addressing: the
-                # device reaches pinned memory under the same pointer): no copy operation behind it
-                self.peers.pull(self.host, stream.cuda_stream)
-                self._pulled = True
-                self._host_is_current = True
-            elif not getattr(self, "_host_is_current", False):
+        stream = self.torch.cuda.current_stream(self.device)
+        if not self._pulled:
+            # the pull kernel writes the 12 words straight into the pinned host block (unified addressing: the
+            # device reaches pinned memory under the same pointer): no copy operation behind it
+            self.peers.pull(self.host, stream.cuda_stream)
+            self._pulled = True
+            self._host_is_current = True
+        elif not getattr(self, "_host_is_current", False):
+            with self.torch.cuda.device(self.device):
                 self.host.copy_(self.acc, non_blocking=True)
-            stream.synchronize()
-        return finalize(p, self.host.numpy().view(np.uint64))
+        stream.synchronize()
+        return finalize(p, self._host_words)
 
     def price(self, workload: str, params, n_paths: int, precision=_lib.F64, seed: int = DEFAULT_SEED) -> OptionValue:
         return self.result(self.enqueue(workload, params, n_paths, precision, seed))

@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 import montecarlocuda_b200 as m
+from montecarlocuda_b200 import _lib as _lib_mod
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
@@ -392,6 +393,44 @@ def test_invalid_arguments_fail_loudly(engine):
         engine.basket(m.MultiOptionData([100.0] * n, [0.2] * n, np.eye(n), [0.0] * n, [1 / n] * n, 100.0, 1.0, 0.05), 1000)
     with pytest.raises(m.Mcb200Error):
         engine.vanilla_paths(VAN, 3, 16, "f32")   # not on a draw-unit boundary
+
+
+def test_duplicate_contexts_are_rejected_not_deadlocked(engine):
+    """mcb200_*_multi locks every context it is given: the same context twice used to deadlock the call on itself."""
+    lib = _lib_mod.load()
+    handles = (C.c_void_p * 2)(engine.handle, engine.handle)
+    r, c = _lib_mod.ResultT(), VAN._c()
+    assert lib.mcb200_vanilla_multi(handles, 2, _lib_mod.F64, C.byref(c), 1 << 16, 1, C.byref(r)) == _lib_mod.ERR_INVALID
+    one = (C.c_void_p * 1)(engine.handle)
+    assert lib.mcb200_vanilla_multi(one, 1, _lib_mod.F64, C.byref(c), 1 << 16, 1, C.byref(r)) == _lib_mod.OK   # the context is still usable
+    assert r.n_paths == 1 << 16
+
+
+def test_high_volatility_many_dates_is_a_valid_cva(engine, oracle):
+    """The range check of the table-driven exponential bounds what a PATH can reach (|ln s/K| + |drift| T + 9 v sqrt(T)),
+    not n times what one step can: 500 dates at 150 % volatility were refused before (n x 9 v sqrt(dt) = 9 v sqrt(n T))."""
+    cva = m.CVA(0.03, 0.6, m.OptionData(100.0, 100.0, 0.05, 1.5, 1.0), 500)
+    r = engine.cva(cva, 1 << 16, "f64")
+    _, keep = oracle.cva_grid(1.0, 500, "f64")
+    closed = oracle.cva_closed_form(100, 100, 0.05, 1.5, 1.0, 0.03, 0.6, 500, keep)
+    assert abs(r.Expected - closed) < 4 * r.std_error + 1e-5
+    vals = engine.cva_paths(cva, 0, 2048, "f64")
+    want = oracle.cva_path_values(100.0, 100.0, 0.05, 1.5, 1.0, 0.03, 0.6, 500, m.api.DEFAULT_SEED, 0, 2048, "f64")
+    assert np.max(np.abs(vals - want) / (1.0 + np.abs(want))) < 1e-10
+    with pytest.raises(m.Mcb200Error):      # ... and what a path really cannot do is still refused
+        engine.cva(m.CVA(0.03, 0.6, m.OptionData(100.0, 100.0, 0.05, 80.0, 1.0), 10), 1000, "f64")
+
+
+def test_kernel_time_is_reported_on_request_only(engine):
+    a = engine.vanilla(VAN, 1 << 20, "f64")
+    assert a.kernel_ms == 0.0
+    engine.set_timing(True)
+    try:
+        b = engine.vanilla(VAN, 1 << 24, "f64")
+        assert 0.01 < b.kernel_ms < 50.0
+    finally:
+        engine.set_timing(False)
+    assert engine.vanilla(VAN, 1 << 20, "f64").Expected == a.Expected
 
 
 def test_degenerate_parameters(engine):

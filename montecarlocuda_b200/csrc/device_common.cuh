@@ -381,12 +381,37 @@ __device__ __forceinline__ void finish(const BlockScratch &sc, unsigned long lon
         st_relaxed_sys(G.host_slot + threadIdx.x, flagged_half(s_tot, threadIdx.x, G.host_flag));
 }
 
+// value -> (sum, sum of squares).  kClamp: v stands for max(v, 0) (a payoff the workload left unclamped).  fp64 has no
+// cheap max (DSETP + selects on the pipe that binds; a sign test with predicated accumulation is turned into four
+// selects by ptxas), so a negative v only has its HIGH word clamped -- one integer max -- which leaves a number below
+// 2^-1042 in place of the zero: its square is exactly 0, and it cannot change a sum that holds anything else (a sum of
+// nothing but such leftovers truncates to zero limbs in lanes_add).  The limbs are those of the exact clamp, which the
+// per-path kernel applies (mc_paths_kernel), and the tests compare the two bit for bit.
+__device__ __forceinline__ bool sign_bit_set(double v) { return __double2hiint(v) < 0; }
+__device__ __forceinline__ bool sign_bit_set(float v) { return __float_as_int(v) < 0; }
+template <bool kClamp>
+__device__ __forceinline__ void add_value(float v, float &s, float &s2)
+{
+    if (kClamp)
+        v = fmaxf(v, 0.0f);
+    s += v;
+    s2 = fmaf(v, v, s2);
+}
+template <bool kClamp>
+__device__ __forceinline__ void add_value(double v, double &s, double &s2)
+{
+    if (kClamp)
+        v = __hiloint2double(max(__double2hiint(v), 0), __double2loint(v));
+    s += v;
+    s2 = fma(v, v, s2);
+}
+
 // One chunk of the job: thread t owns units base + k * 256 + t for k < rounds, in that order, and accumulates value
 // and value^2 in W::Real (short runs: at most rounds * kUnitPaths <= 384 terms) before the fp64 block reduction.
 template <class W>
 __device__ __forceinline__ void run_chunk(const typename W::Params &P, const JobGeometry &G, unsigned long long chunk, int tid,
-                                          const typename W::Shared &sh, typename W::Real &s_out, typename W::Real &s2_out,
-                                          unsigned long long &n_valid)
+                                          const typename W::Shared &sh, const typename W::JobState &job,
+                                          typename W::Real &s_out, typename W::Real &s2_out, unsigned long long &n_valid)
 {
     using Real = typename W::Real;
     const unsigned long long base = chunk * G.chunk_units;
@@ -408,12 +433,10 @@ __device__ __forceinline__ void run_chunk(const typename W::Params &P, const Job
             if (W::kUnitPaths == 1 && !whole && unit >= G.total_paths)
                 break;
             Real v[W::kUnitPaths];
-            W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh);
+            W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh, job);
 #pragma unroll
-            for (int q = 0; q < W::kUnitPaths; q++) {
-                s += v[q];
-                s2 = fma(v[q], v[q], s2);
-            }
+            for (int q = 0; q < W::kUnitPaths; q++)
+                add_value<W::kClampAtZero>(v[q], s, s2);
         }
     } else {
         // the job's last chunk with several paths per unit: mask paths beyond the total
@@ -423,13 +446,11 @@ __device__ __forceinline__ void run_chunk(const typename W::Params &P, const Job
             if (unit * (unsigned long long)W::kUnitPaths >= G.total_paths)
                 break;
             Real v[W::kUnitPaths];
-            W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh);
+            W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh, job);
 #pragma unroll
             for (int q = 0; q < W::kUnitPaths; q++) {
-                if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths) {
-                    s += v[q];
-                    s2 = fma(v[q], v[q], s2);
-                }
+                if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths)
+                    add_value<W::kClampAtZero>(v[q], s, s2);
             }
         }
     }
@@ -443,7 +464,10 @@ __device__ __forceinline__ void run_chunk(const typename W::Params &P, const Job
 //   W::kUnitPaths      paths served by one draw unit
 //   W::kMinBlocks      CTAs per SM the register budget is sized for; W::kUnroll  unroll of the unit loop
 //   W::Shared          per-CTA shared-memory state (the fp64 math tables; empty for fp32)
-//   W::eval(P, unit_lo, unit_hi, v, sh) fills v[kUnitPaths] with the per-path values of a draw unit;
+//   W::JobState        per-job shared-memory state of one sub-block (fp64: the exponent table of the job's scaled
+//                      logarithm; empty for fp32), filled by W::prepare(P, job, tid)
+//   W::kClampAtZero    the per-path value is max(v, 0) of what eval returns (add_value clamps for free)
+//   W::eval(P, unit_lo, unit_hi, v, sh, job) fills v[kUnitPaths] with the per-path values of a draw unit;
 //                      inside a chunk unit_hi is the same for every thread (chunks are aligned), so the
 //                      part of the first two Philox rounds that depends only on it runs on the uniform datapath
 // Persistent CTAs; every sub-block of 256 threads walks chunks of the shard (ChunkWalk) through run_chunk.
@@ -459,11 +483,13 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
     extern __shared__ __align__(16) unsigned char mcb_dynamic_smem[];
     typename W::Shared &sh = *reinterpret_cast<typename W::Shared *>(mcb_dynamic_smem);
     __shared__ BlockScratch scs[kSub];
+    __shared__ typename W::JobState jobs[kSub];
     // sub-block = the "block" of the stream definition: kThreads threads, its own scratch, its own chunks
     const int sub = kSub == 1 ? 0 : (int)(threadIdx.x / kThreads);
     const int tid = kSub == 1 ? (int)threadIdx.x : (int)(threadIdx.x % kThreads);
     BlockScratch &sc = scs[sub];
     sh.load();
+    W::prepare(P, jobs[sub], tid);
     if (tid < kAccWords)
         sc.acc[tid] = 0ull;
     __syncthreads();
@@ -471,7 +497,7 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
         walk.claim_ahead(G, tid);
         Real s, s2;
         unsigned long long n_valid;
-        run_chunk<W>(P, G, G.first_chunk + walk.chunk, tid, sh, s, s2, n_valid);
+        run_chunk<W>(P, G, G.first_chunk + walk.chunk, tid, sh, jobs[sub], s, s2, n_valid);
         chunk_commit<kSub>((double)s, (double)s2, n_valid, G, sc, sub, tid, walk.ahead);
     }
     if constexpr (kSub > 1)
@@ -512,11 +538,13 @@ mc_accumulate_batch_kernel(const __grid_constant__ BatchJobs<W> B)
     extern __shared__ __align__(16) unsigned char mcb_dynamic_smem[];
     typename W::Shared &sh = *reinterpret_cast<typename W::Shared *>(mcb_dynamic_smem);
     __shared__ BlockScratch scs[kSub];
+    __shared__ typename W::JobState jobs[kSub];
     __shared__ bool s_last;
     const int sub = kSub == 1 ? 0 : (int)(threadIdx.x / kThreads);
     const int tid = kSub == 1 ? (int)threadIdx.x : (int)(threadIdx.x % kThreads);
     BlockScratch &sc = scs[sub];
     sh.load();
+    W::prepare(B.params[0], jobs[sub], tid);
     if (tid < kAccWords)
         sc.acc[tid] = 0ull;
     __syncthreads();
@@ -537,10 +565,14 @@ mc_accumulate_batch_kernel(const __grid_constant__ BatchJobs<W> B)
             if (tid < kAccWords)
                 sc.acc[tid] = 0ull;
             job = j;
+            // the sub-block's per-job state follows (everybody is past the previous chunk's last barrier)
+            W::prepare(B.params[job], jobs[sub], tid);
+            if constexpr (!std::is_empty<typename W::JobState>::value)
+                sub_barrier<kSub>(sub);
         }
         Real s, s2;
         unsigned long long n_valid;
-        run_chunk<W>(B.params[job], B.geo[job], (unsigned long long)(chunk - B.first[job]), tid, sh, s, s2, n_valid);
+        run_chunk<W>(B.params[job], B.geo[job], (unsigned long long)(chunk - B.first[job]), tid, sh, jobs[sub], s, s2, n_valid);
         chunk_commit<kSub>((double)s, (double)s2, n_valid, B.geo[job], sc, sub, tid, ahead);
         chunk = sc.next;
     }
@@ -669,15 +701,17 @@ mc_paths_kernel(const __grid_constant__ typename W::Params P, unsigned long long
                 unsigned long long n_units, typename W::Real *__restrict__ out)
 {
     __shared__ typename W::Shared sh;
+    __shared__ typename W::JobState job;
     sh.load();
+    W::prepare(P, job, (int)threadIdx.x);
     __syncthreads();
     for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < n_units;
          i += (unsigned long long)gridDim.x * kThreads) {
         typename W::Real v[W::kUnitPaths];
-        W::eval(P, (uint32_t)(first_unit + i), (uint32_t)((first_unit + i) >> 32), v, sh);
+        W::eval(P, (uint32_t)(first_unit + i), (uint32_t)((first_unit + i) >> 32), v, sh, job);
 #pragma unroll
         for (int q = 0; q < W::kUnitPaths; q++)
-            out[i * W::kUnitPaths + q] = v[q];
+            out[i * W::kUnitPaths + q] = (W::kClampAtZero && sign_bit_set(v[q])) ? (typename W::Real)0 : v[q];
     }
 }
 

@@ -14,7 +14,7 @@
 namespace mcb {
 
 // Per-CTA shared-memory state of a workload: nothing for fp32 (every special function is a MUFU
-// op), the log / exp tables for fp64.  load() is called by all threads of the CTA before the
+// op), the log / exp / angle tables for fp64.  load() is called by all threads of the CTA before the
 // first barrier of the kernel.
 struct NoShared {
     __device__ __forceinline__ void load() {}
@@ -23,43 +23,27 @@ struct SharedTables64 {
     Tables64 t;
     __device__ __forceinline__ void load()
     {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-            t.log_tab[i][0] = kLogTable[i][0];
-            t.log_tab[i][1] = kLogTable[i][1];
-            t.exp_tab[i] = kExpTable[i];
-        }
-        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-            t.turn_hi[i][0] = kTurnHiTable[i][0];
-            t.turn_hi[i][1] = kTurnHiTable[i][1];
-            t.turn_lo[i][0] = kTurnLoTable[i][0];
-            t.turn_lo[i][1] = kTurnLoTable[i][1];
-        }
+        for (int i = threadIdx.x; i < 256; i += blockDim.x)
+            t.fill(i);
     }
 };
 // the same tables in the bank-conflict-free layout (device_math64.cuh), for the pricing kernels
-__device__ __forceinline__ void load_tables_rep(Tables64Rep &t)
-{
-    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-        t.log_rep[i >> 3][i & 7][0] = kLogTable[i >> 3][0];
-        t.log_rep[i >> 3][i & 7][1] = kLogTable[i >> 3][1];
-    }
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x)
-        t.exp_rep[i >> 4][i & 15] = kExpTable[i >> 4];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-        t.turn_hi[i][0] = kTurnHiTable[i][0];
-        t.turn_hi[i][1] = kTurnHiTable[i][1];
-        t.turn_lo[i][0] = kTurnLoTable[i][0];
-        t.turn_lo[i][1] = kTurnLoTable[i][1];
-    }
-}
 struct SharedTables64Rep {
     Tables64Rep t;
-    __device__ __forceinline__ void load() { load_tables_rep(t); }
-};
-// ... and with the math constants taken from the constant bank (register-capped kernels: CVA)
-struct SharedTables64RepBank {
-    Tables64RepBank t;
-    __device__ __forceinline__ void load() { load_tables_rep(t); }
+    __device__ __forceinline__ void load()
+    {
+        for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+            const int j = i >> 3, rep = i & 7;
+            t.log_rep[j][rep][0] = bias_log_recip(kLogTable[j][0]);
+            t.log_rep[j][rep][1] = kLogTable[j][1];
+            t.turn_lo_rep[j][rep][0] = kTurnLoTable[j][0];
+            t.turn_lo_rep[j][rep][1] = kTurnLoTable[j][1];
+        }
+        for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x)
+            t.exp_rep[i >> 4][i & 15] = bias_exp_entry(kExpTable[i >> 4], i >> 4);
+        for (int i = threadIdx.x; i < 4096; i += blockDim.x)
+            *reinterpret_cast<double2 *>(t.turn_hi[i]) = *reinterpret_cast<const double2 *>(kTurnHiTable[i]);
+    }
 };
 template <typename Real> struct SharedFor;
 template <> struct SharedFor<float> { using type = NoShared; };
@@ -67,6 +51,16 @@ template <> struct SharedFor<double> { using type = SharedTables64; };
 // what mc_accumulate_kernel instantiates a workload with
 template <typename Real> struct SharedAccumFor { using type = typename SharedFor<Real>::type; };
 template <> struct SharedAccumFor<double> { using type = SharedTables64Rep; };
+
+// Per-JOB shared-memory state, one per sub-block of 256 threads (the sub-blocks of a sweep launch may be working on
+// different jobs): nothing for fp32; for fp64 the exponent table of the job's scaled logarithm (LogScale64).
+// W::prepare(P, job_state, tid) fills it; the kernel puts a sub-block barrier behind it.
+struct NoJobState {
+    __device__ __forceinline__ void fill(int, float) {}
+};
+template <typename Real> struct JobStateFor;
+template <> struct JobStateFor<float> { using type = NoJobState; };
+template <> struct JobStateFor<double> { using type = LogScale64; };
 
 // ---- fp32: every transcendental is ONE MUFU op (no denormal fix-up, no range-reduction code) ----
 __device__ __forceinline__ float mufu_lg2(float x)
@@ -162,38 +156,45 @@ __device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float
 // the other 20 (a turn fraction k / 2^20: 2^20 directions; for anything smooth in the pair the
 // lattice error is that of a trapezoid rule on a periodic function, i.e. far below fp64 rounding).
 // The first version spent a whole block per pair (52-bit radius and angle): twice the IMAD.WIDE
-// work for bits no estimate can see.  All arithmetic after the bits is fp64: 12 (log) + 7 (sqrt) +
-// 4 (cos/sin from the two-level table) + 2 = 25 fp64 instructions per pair (libdevice: 68+).
+// work for bits no estimate can see.  All arithmetic after the bits is fp64: 1 (2 - f) + 9 (log) + 5 or 7 (sqrt) +
+// 4 (cos/sin from the two-level table) [+ 2 for z = r cos, r sin] fp64 instructions per pair (libdevice: 68+).
 // No |.| around the logarithm: u = 2 - f is a multiple of 2^-44, so k ln u is either the tiny positive offset (u == 1)
 // or at least 2^-43 |k| / 2 -- four orders of magnitude above the function's rounding error (checked on the host over
 // every u = 1 - j 2^-44, j <= 2e6: min 1.1366e-13, error 2.7e-17).  With a 52-bit radius it could come out as -1e-17,
-// and the fabs cost an fp64 instruction per pair (MUFU.RSQ64H cannot take an operand modifier).  Bit-identical
-// values; basket-10 7.20 -> 7.12 ms, CVA 16.93 -> 16.61 ms.  The European call is the exception: 0.3 % FASTER with the
-// extra instruction (9.711 vs 9.740 ms, profiles/r01p_ab_experiments.txt), so polar_from_words keeps it there.
-template <class Tab>
-__device__ __forceinline__ void box_muller_f64(uint32_t wa, uint32_t wb, double &z0, double &z1, const Tab &T)
+// and the fabs cost an fp64 instruction per pair (MUFU.RSQ64H cannot take an operand modifier).
+__device__ __forceinline__ double radius_uniform_f64(uint32_t wa, uint32_t wb)
 {
     const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
-    const double r = sqrt_pos<true>(neg2log_unit(2.0 - f, T));
+    return 2.0 - f;
+}
+template <class Tab>
+__device__ __forceinline__ void box_muller_f64(uint32_t wa, uint32_t wb, double &z0, double &z1, const Tab &T, const LogScale64 &S)
+{
+    const double r = sqrt_pos<true>(neg2log_unit(radius_uniform_f64(wa, wb), T, S));
     double cs, sn;
-    sincos_turn20(wb & 0x000fffffu, cs, sn, T);
+    sincos_turn20(wb, cs, sn, T);
     z0 = r * cs;
     z1 = r * sn;
 }
 
+// S: LogScale64 filled with -2 ln 2 (polar_scale(1))
 template <class Sh>
-__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], double (&z)[4], const Sh &sh)
+__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], double (&z)[4], const Sh &sh, const LogScale64 &S)
 {
-    box_muller_f64(w[0], w[1], z[0], z[1], sh.t);
-    box_muller_f64(w[2], w[3], z[2], z[3], sh.t);
+    box_muller_f64(w[0], w[1], z[0], z[1], sh.t, S);
+    box_muller_f64(w[2], w[3], z[2], z[3], sh.t, S);
+}
+__device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float (&z)[6], const NoShared &sh, const NoJobState &)
+{
+    normals_from_words(w, z, sh);
 }
 
 // ---- scaled polar form of a block's Box-Muller pairs ---------------------------------------------------
 // A caller that only needs b z (a diffusion step, an exponent), never z itself, takes the pairs as
 // (b r, cos, sin): b z0 = (b r) cos, b z1 = (b r) sin fold into the FMA that consumes them, and the scale b
 // costs nothing because it rides on constants that are there anyway -- fp32: b r = sqrt(lg2(u) * c) with
-// c = -2 ln2 b^2; fp64: b^2 (-2 ln u) = scaled_log_unit(u, c, c_ln2) with c = -2 b^2, c_ln2 = c ln 2.
-// Saves the two multiplies r cos, r sin of every pair.
+// c = -2 ln2 b^2; fp64: b^2 (-2 ln u) = scaled_log_unit(u, c, S) with c = -2 b^2 and the job's exponent table S
+// filled with c ln 2.  Saves the two multiplies r cos, r sin of every pair.
 template <typename Real> struct PolarScale {
     Real c, c_ln2;
 };
@@ -209,9 +210,16 @@ template <typename Real> __host__ __device__ inline PolarScale<Real> polar_scale
     }
     return s;
 }
-template <bool kShortSqrt = false>
+// the per-job state of a workload whose normals are scaled by S (W::prepare)
+__device__ __forceinline__ void prepare_polar(const PolarScale<float> &, NoJobState &, int) {}
+__device__ __forceinline__ void prepare_polar(const PolarScale<double> &S, LogScale64 &job, int tid)
+{
+    if (tid < 64)
+        job.fill(tid, S.c_ln2);
+}
+template <bool kShortSqrt = true>
 __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], float (&br)[3], float (&cs)[3], float (&sn)[3],
-                                                 const NoShared &, const PolarScale<float> &S)
+                                                 const NoShared &, const PolarScale<float> &S, const NoJobState &)
 {
     float f[6];
     uniforms_f32(w, f);
@@ -223,17 +231,14 @@ __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], float (
         sn[i] = mufu_sin(ang);
     }
 }
-template <bool kShortSqrt = false, class Sh>
+template <bool kShortSqrt = true, class Sh>
 __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], double (&br)[2], double (&cs)[2], double (&sn)[2],
-                                                 const Sh &sh, const PolarScale<double> &S)
+                                                 const Sh &sh, const PolarScale<double> &S, const LogScale64 &job)
 {
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const uint32_t wa = w[2 * i], wb = w[2 * i + 1];
-        const double f = __hiloint2double((int)(0x3ff00000u | (wa >> 12)), (int)((wa << 20) | ((wb >> 12) & 0x000fff00u)));
-        const double r2 = scaled_log_unit(2.0 - f, sh.t, S.c, S.c_ln2);
-        br[i] = sqrt_pos<kShortSqrt>(kShortSqrt ? r2 : fabs(r2));  // kShortSqrt == false: the European call (see box_muller_f64)
-        sincos_turn20(wb & 0x000fffffu, cs[i], sn[i], sh.t);
+        br[i] = sqrt_pos<kShortSqrt>(scaled_log_unit(radius_uniform_f64(w[2 * i], w[2 * i + 1]), sh.t, S.c, job));
+        sincos_turn20(w[2 * i + 1], cs[i], sn[i], sh.t);
     }
 }
 
@@ -246,7 +251,14 @@ template <> struct NormalsPerBlock<double> { static constexpr int value = 4; };
 __device__ __forceinline__ float positive_part(float x) { return fmaxf(x, 0.0f); }
 __device__ __forceinline__ double positive_part(double x) { return relu64(x); }
 
-// precision-generic wrappers used by the workload policies
+// precision-generic wrappers used by the workload policies.  exp_scaled takes its argument in the units the
+// exponential is cheapest in -- log2 units for fp32 (MUFU.EX2), units of ln2/256 for fp64 (exp_units) -- and
+// kExpUnit<Real> is the factor that takes a natural-log quantity there (the host folds it into the job's constants).
+template <typename Real> struct ExpUnit;
+template <> struct ExpUnit<float> { static constexpr double value = 1.4426950408889634074; };           // 1 / ln 2
+template <> struct ExpUnit<double> { static constexpr double value = 369.32993046757463228; };           // 256 / ln 2
+template <class Sh> __device__ __forceinline__ float exp_scaled(float x, const Sh &) { return mufu_ex2(x); }
+template <class Sh> __device__ __forceinline__ double exp_scaled(double y, const Sh &sh) { return exp_units(y, sh.t); }
 __device__ __forceinline__ float exp_real(float x, const NoShared &) { return mufu_ex2(x * 1.4426950408889634f); }
 template <class Sh> __device__ __forceinline__ double exp_real(double x, const Sh &sh) { return exp_tab(x, sh.t); }
 __device__ __forceinline__ float rcp_real(float x) { return mufu_rcp(x); }

@@ -3,13 +3,16 @@
 // libdevice's log / sincospi / exp / division cost 30 / 27 / 18 / 8+ fp64 instructions plus as many
 // integer ones (measured: 162 warp-instructions per vanilla path, profiles/r01a_*).  Here:
 //
-//   neg2log_unit   -2 ln(u), u in (0,1]   table of 256 reciprocals (shared memory) + degree-6 log1p   9 fp64
-//   sqrt_pos       sqrt(x)                MUFU.RSQ64H seed + 2 coupled Newton steps (or 1 + a correction) 7 / 5 fp64
-//   sincos_turn    cos/sin(2 pi k/2^52)   octant taken from the integer bits (exact reduction),
-//                                         fdlibm kernel polynomials on [0, pi/4]                     18 fp64
-//   exp_tab        e^x                    n = rint(256 x / ln2) by magic add, Cody-Waite, table of
-//                                         2^(j/256), degree-4 expm1, exponent added as an integer     9 fp64
-//   rcp_newton     1/x                    MUFU.RCP64H seed + 1 cubic step                             3 fp64
+//   scaled_log_unit  k ln(u), u in (0,1]  table of 256 reciprocals (shared memory) + degree-6 log1p; the exponent's
+//                                          share comes from a 64-entry table per job (LogScale64)          9 fp64
+//   sqrt_pos         sqrt(x)               MUFU.RSQ64H seed + 2 coupled Newton steps (or 1 + a correction) 7 / 5 fp64
+//   sincos_turn20    cos/sin(2 pi k/2^20)  two-level table (12 + 8 bits) and the addition theorems         4 fp64
+//   sincos_turn      cos/sin(2 pi k/2^52)  octant taken from the integer bits (exact reduction),
+//                                          fdlibm kernel polynomials on [0, pi/4] (tests only)             18 fp64
+//   exp_units        2^(y/256)             n = rint(y) by magic add, r = y - n exactly, table of 2^(j/256) with
+//                                          the exponent added as an integer, degree-4 expm1               8 fp64
+//   exp_tab          e^x                   the same behind a Cody-Waite reduction                         10 fp64
+//   rcp_newton       1/x                   MUFU.RCP64H seed + 1 cubic step                                 3 fp64
 //
 // Accuracy (checked on the CPU against libm by tests/test_device_math64.py through the host build
 // of this very header, and on the GPU against the oracle): <= 2 ulp for exp/sqrt/rcp/sincos,
@@ -41,36 +44,6 @@ namespace hostmath {
 
 #include "tables64.inc"
 
-// Polynomial and reduction constants that do not fit an instruction's immediate field (an fp64 immediate is the
-// high word only).  Written as literals, ptxas re-materialises each use with two MOVs -- in the register-capped CVA
-// kernel that was 38 of the 167 instructions of a path-step (profiles/r01k_cva50_f64_2p26.txt: UMOV 20, IMAD.MOV 12,
-// LDC 6 per step).  From the constant bank they are plain DFMA operands (CVA 20.4 -> 19.8 ms).  Kernels with
-// registers to spare keep the literals: there ptxas holds them in registers across the loop and the constant-bank
-// operands are slower (vanilla fp64 9.72 -> 10.36 ms when forced), so the choice rides on the table type
-// (Tab::kConstBank) the kernel instantiates the functions with.  Since the CVA kernel runs 2 sub-blocks of 256 threads
-// (128 registers) it keeps the literals too (16.92 vs 17.01 ms); the constant-bank route stays selectable
-// (MCB_CVA_BANK=1 together with MCB_CVA_SUBBLOCKS=3, kernels_cva.cu).
-struct MathConsts64 {
-    double log_magic;          // 2^52 + 1023
-    double log_c6, log_c5, log_c3;   // -1/6, 1/5, 1/3   (-1/4, -1/2 are immediates)
-    double neg2ln2;            // -2 ln 2
-    double tiny;               // 1e-300
-    double exp_scale;          // 256 / ln 2
-    double exp_ln2_hi, exp_ln2_lo;   // -ln2/256 split (Cody-Waite)
-    double exp_c4, exp_c3;     // 1/24, 1/6
-    double inv_sqrt_2pi;
-    double hast_k, hast_a1, hast_a2, hast_a3, hast_a4, hast_a5;
-};
-#define MCB_MATH_CONSTS_INIT                                                                                             \
-    {4503599627371519.0, -1.0 / 6.0, 0.2, 1.0 / 3.0, -2.0 * 0x1.62e42fefa39efp-1, 1e-300, 0x1.71547652b82fep+8,           \
-     -0x1.62e42fee00000p-9, -0x1.a39ef35793c76p-41, 1.0 / 24.0, 1.0 / 6.0, 0.39894228040143267793994605993438, 0.2316419,   \
-     0.31938153, -0.356563782, 1.781477937, -1.821255978, 1.330274429}
-#ifdef MCB_HOST_MATH
-static const MathConsts64 kMathConsts64 = MCB_MATH_CONSTS_INIT;
-#else
-static __constant__ MathConsts64 kMathConsts64 = MCB_MATH_CONSTS_INIT;
-#endif
-
 // ---- bit access and the two MUFU seeds -----------------------------------------------------------
 #ifdef MCB_HOST_MATH
 MCB_FN int hi_word(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
@@ -89,6 +62,7 @@ MCB_FN double fma_(double a, double b, double c) { return std::fma(a, b, c); }
 MCB_FN double seed_trunc(double y) { return make_double(hi_word(y), 0); }
 MCB_FN double rsqrt_seed(double x) { return seed_trunc(1.0 / std::sqrt(make_double(hi_word(x), 0))); }
 MCB_FN double rcp_seed(double x) { return seed_trunc(1.0 / make_double(hi_word(x), 0)); }
+MCB_FN uint32_t and_or(uint32_t a, uint32_t mask, uint32_t c) { return (a & mask) | c; }
 #else
 MCB_FN int hi_word(double x) { return __double2hiint(x); }
 MCB_FN int lo_word(double x) { return __double2loint(x); }
@@ -106,119 +80,169 @@ MCB_FN double rcp_seed(double x)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     return y;
 }
+// (a & mask) | c as ONE LOP3: a table offset "index field of a word, plus this thread's replica" costs a shift and
+// this, where base + replica + (index << s) written as pointer arithmetic compiled to shift, mask, add
+MCB_FN uint32_t and_or(uint32_t a, uint32_t mask, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(c));
+    return d;
+}
 #endif
 
-// The tables live in shared memory inside the kernels (random per-thread indices: a constant-bank
-// read would serialise); this is the view the functions take.  Plain layout: host build, instrumentation
-// and per-path kernels.
-#define MCB_K(Tab, field, literal) (Tab::kConstBank ? kMathConsts64.field : (literal))
+// ---- the tables as the kernels hold them in shared memory ------------------------------------------
+// (random per-thread indices: a constant-bank read would serialise).  Two of the generated tables are kept in a
+// form that saves integer work per look-up:
+//   log:  c_i carries the exponent bias of 1.0 on top of its own exponent field (high word + 0x3ff00000), so that
+//         subtracting u's exponent field from it is c_i 2^-e -- the reciprocal for u itself, not for its mantissa
+//         taken out and re-biased (one LOP3 + one integer add where building m = u 2^-e took three instructions);
+//   exp:  2^(j/256) has j << 12 subtracted from its high word, so that adding n << 12 for n = 256 k + j gives
+//         2^k 2^(j/256) = 2^(n/256) in one integer instruction (shift, mask and add on the result before).
+// Neither is a valid double on its own; both changes are exact, the values the functions return did not change.
+MCB_FN double bias_log_recip(double c) { return make_double(hi_word(c) + 0x3ff00000, lo_word(c)); }
+MCB_FN double bias_exp_entry(double t, int j) { return make_double(hi_word(t) - (j << 12), lo_word(t)); }
+
+// Plain layout: host build, instrumentation and per-path kernels (their coarse angle table stays where the
+// generated one lies -- global memory on the device: 64 KB do not fit a static shared-memory allocation).
 struct Tables64 {
-    static constexpr bool kConstBank = false;
-    double log_tab[256][2];       // { c_i, -ln c_i }
-    double exp_tab[256];          // 2^(j/256)
-    double turn_hi[1024][2];      // { cos, sin } of 2 pi i / 1024
-    double turn_lo[1024][2];      // { cos, sin } of 2 pi j / 2^20
-    MCB_MEMBER void log_entry(int i, double &c, double &l) const { c = log_tab[i][0]; l = log_tab[i][1]; }
-    MCB_MEMBER double exp_entry(int j) const { return exp_tab[j]; }
-    MCB_MEMBER void turn_hi_entry(uint32_t i, double &c, double &s) const { c = turn_hi[i][0]; s = turn_hi[i][1]; }
-    MCB_MEMBER void turn_lo_entry(uint32_t j, double &c, double &s) const { c = turn_lo[j][0]; s = turn_lo[j][1]; }
+    double log_tab[256][2];       // { c_i (biased), -ln c_i }
+    double exp_tab[256];          // 2^(j/256) (biased)
+    double turn_lo[256][2];       // { cos, sin } of 2 pi j / 2^20
+    // hi_u = high word of u: the entry of its top 8 mantissa bits
+    MCB_MEMBER void log_entry(int hi_u, double &c, double &l) const
+    {
+        const int i = (hi_u >> 12) & 0xff;
+        c = log_tab[i][0];
+        l = log_tab[i][1];
+    }
+    MCB_MEMBER double exp_entry(int n) const { return exp_tab[n & 255]; }
+    // k = a 20-bit turn fraction (higher bits ignored): coarse entry of its top 12 bits, fine entry of its low 8
+    MCB_MEMBER void turn_hi_entry(uint32_t k, double &c, double &s) const { c = kTurnHiTable[(k >> 8) & 4095u][0]; s = kTurnHiTable[(k >> 8) & 4095u][1]; }
+    MCB_MEMBER void turn_lo_entry(uint32_t k, double &c, double &s) const { c = turn_lo[k & 255u][0]; s = turn_lo[k & 255u][1]; }
+    MCB_MEMBER void fill(int i)   // for every i < 256
+    {
+        log_tab[i][0] = bias_log_recip(kLogTable[i][0]);
+        log_tab[i][1] = kLogTable[i][1];
+        exp_tab[i] = bias_exp_entry(kExpTable[i], i);
+        turn_lo[i][0] = kTurnLoTable[i][0];
+        turn_lo[i][1] = kTurnLoTable[i][1];
+    }
+};
+
+// The plain layout with the coarse angle table in shared memory as well (the two-pass wide-basket kernel).
+struct Tables64Wide : Tables64 {
+    double turn_hi[4096][2];
+    MCB_MEMBER void turn_hi_entry(uint32_t k, double &c, double &s) const { c = turn_hi[(k >> 8) & 4095u][0]; s = turn_hi[(k >> 8) & 4095u][1]; }
+    MCB_MEMBER void fill_wide(int i)   // for every i < 4096
+    {
+        if (i < 256)
+            fill(i);
+        turn_hi[i][0] = kTurnHiTable[i][0];
+        turn_hi[i][1] = kTurnHiTable[i][1];
+    }
 };
 
 #ifndef MCB_HOST_MATH
 // Bank-conflict-free layout for the pricing kernels.  The indices are random per thread, so in the plain layout
 // the 8 threads of a quarter-warp (16-byte loads) or the 16 of a half-warp (8-byte loads) collide in the 32
-// shared-memory banks: ~2.7 wavefronts where 1 would do.  ncu on the plain layout (profiles/r01j_vanilla_f64_2p32.txt):
+// shared-memory banks: ~2.6 wavefronts where 1 would do.  ncu on the plain layout (profiles/r01j_vanilla_f64_2p32.txt):
 // 62 % of all shared-memory wavefronts were bank conflicts and the shared-memory pipe was 97 % busy -- the
-// European-call fp64 kernel was bound by it, not by the fp64 pipe.  Here the two small tables are replicated once
+// European-call fp64 kernel was bound by it, not by the fp64 pipe.  Here the small tables are replicated once
 // per bank group: thread t reads replica t % 8 (16-byte entries: 128 bytes per index, one bank group per replica)
 // or t % 16 (8-byte entries), so threads that are served together can never share a bank.  Same values, same
-// arithmetic, bit-identical results; 64 KB instead of 6 KB, shared by all warps of a (large) CTA.
-// The two angle tables (16 KB each) stay single copies: 2.6 wavefronts per quarter-warp instead of 1 (22 of the 29
-// wavefronts of a Box-Muller pair).  Four copies each (thread t reads replica t % 4: 1.9 wavefronts per quarter-warp,
-// 192 KB in all) were measured and are SLOWER -- European call 10.15 vs 9.73 ms, basket-10 7.26 vs 7.21 ms
-// (profiles/r01p_ab_experiments.txt): once log and exp were conflict-free the shared-memory pipe stopped being what
-// binds, and the wider index arithmetic costs more than the wavefronts give back.
+// arithmetic, bit-identical results.
+// The angle is split 12 + 8 bits so that its FINE table (256 entries) is small enough to be replicated as well; the
+// coarse one (4096 entries, 64 KB) stays a single copy at 2.6 wavefronts per quarter-warp.  With the 10 + 10 split of
+// round 1 (two single 16 KB tables) the angle look-ups were 22 of the 29 wavefronts of a Box-Muller pair and the
+// shared-memory pipe the busiest unit of the fp64 call (68 %) and the 10-asset basket (79 %); four copies of each
+// (192 KB) had been measured slower (profiles/r01p_ab_experiments.txt) -- with pointer arithmetic, not the one-LOP3
+// offsets used here.  160 KB in all, one table set per SM shared by the CTA's sub-blocks.
 struct Tables64Rep {
-    static constexpr bool kConstBank = false;
-    double log_rep[256][8][2];    // [index][replica]{ c_i, -ln c_i }
-    double exp_rep[256][16];      // [index][replica] 2^(j/256)
-    double turn_hi[1024][2];
-    double turn_lo[1024][2];
-    MCB_MEMBER void log_entry(int i, double &c, double &l) const
+    double log_rep[256][8][2];       // [index][replica]{ c_i (biased), -ln c_i }        32 KB
+    double exp_rep[256][16];         // [index][replica] 2^(j/256) (biased)             32 KB
+    double turn_lo_rep[256][8][2];   // [index][replica]{ cos, sin } of 2 pi j / 2^20   32 KB
+    double turn_hi[4096][2];         // { cos, sin } of 2 pi i / 4096                   64 KB
+    MCB_MEMBER void log_entry(int hi_u, double &c, double &l) const
     {
-        const double2 v = *reinterpret_cast<const double2 *>(&log_rep[i][threadIdx.x & 7][0]);
+        const uint32_t off = and_or((uint32_t)hi_u >> 5, 0x7f80u, (threadIdx.x & 7u) << 4);
+        const double2 v = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(log_rep) + off);
         c = v.x;
         l = v.y;
     }
-    MCB_MEMBER double exp_entry(int j) const { return exp_rep[j][threadIdx.x & 15]; }
-    MCB_MEMBER void turn_hi_entry(uint32_t i, double &c, double &s) const { c = turn_hi[i][0]; s = turn_hi[i][1]; }
-    MCB_MEMBER void turn_lo_entry(uint32_t j, double &c, double &s) const { c = turn_lo[j][0]; s = turn_lo[j][1]; }
-};
-struct Tables64RepBank : Tables64Rep {   // same layout; the functions take their constants from the constant bank
-    static constexpr bool kConstBank = true;
+    MCB_MEMBER double exp_entry(int n) const
+    {
+        const uint32_t off = and_or((uint32_t)n << 7, 0x7f80u, (threadIdx.x & 15u) << 3);
+        return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(exp_rep) + off);
+    }
+    MCB_MEMBER void turn_hi_entry(uint32_t k, double &c, double &s) const
+    {
+        const double2 v = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(turn_hi) + ((k >> 4) & 0xfff0u));
+        c = v.x;
+        s = v.y;
+    }
+    MCB_MEMBER void turn_lo_entry(uint32_t k, double &c, double &s) const
+    {
+        const uint32_t off = and_or(k << 7, 0x7f80u, (threadIdx.x & 7u) << 4);
+        const double2 v = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(turn_lo_rep) + off);
+        c = v.x;
+        s = v.y;
+    }
 };
 #endif
 
+// The exponent part of a scaled logarithm, per job: entry (E & 63) = (E - 1023) k ln 2 + 1e-300 for the biased
+// exponent E of u in [2^-63, 1] (the kernels' radius uniform is >= 2^-44).  One 8-byte load replaces the conversion
+// of the exponent (an fp64 subtract of a magic number) and its FMA.  The tiny offset keeps k ln u away from an exact
+// 0 at u == 1, so the square root after it needs no zero guard.  64 entries: a sub-block's threads 0..63 fill it.
+struct LogScale64 {
+    double e[64];
+    MCB_MEMBER void fill(int i, double k_ln2) { e[i] = fma_((double)(i - 63), k_ln2, 1e-300); }
+    // ebits = u's exponent field in place (high word & 0x7ff00000)
+    MCB_MEMBER double entry(int ebits) const
+    {
+        return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(e) + (((uint32_t)ebits >> 17) - (960u << 3)));
+    }
+};
+
 // ---- cos and sin of 2 pi k / 2^20 for a 20-bit integer k (the Box-Muller angle of the kernels) ---
-// Two-level table: k = 1024 i + j, angle = coarse_i + fine_j, and the addition theorems give the
+// Two-level table: k = 256 i + j, angle = coarse_i + fine_j, and the addition theorems give the
 // result from four correctly rounded table values with 2 multiplies + 2 FMAs (abs error < 2 ulp of
 // 1).  Two 16-byte shared-memory loads replace 19 fp64 and ~20 integer instructions of the
 // polynomial version below (sincos_turn), which stays as the reference implementation in the tests.
+// Bits of k above the 20th are ignored.
 template <class Tab> MCB_FN void sincos_turn20(uint32_t k, double &cs, double &sn, const Tab &T)
 {
-    const uint32_t i = (k >> 10) & 1023u, j = k & 1023u;
     double ch, sh, cl, sl;
-    T.turn_hi_entry(i, ch, sh);
-    T.turn_lo_entry(j, cl, sl);
+    T.turn_hi_entry(k, ch, sh);
+    T.turn_lo_entry(k, cl, sl);
     cs = fma_(-sh, sl, ch * cl);
     sn = fma_(ch, sl, sh * cl);
 }
 
-// ---- -2 ln(u) for u in (0, 1] --------------------------------------------------------------------
-// u = 2^e m, m in [1,2); i = top 8 mantissa bits; r = m c_i - 1 in [0, 2^-8);
+// ---- k ln(u) for u in [2^-63, 1] and a caller-chosen k ---------------------------------------------
+// u = 2^e m, m in [1,2); i = top 8 mantissa bits; r = m c_i - 1 = u (c_i 2^-e) - 1 in [0, 2^-8);
 // ln u = e ln2 + (-ln c_i) + log1p(r), log1p by its degree-6 Taylor polynomial (|error| < 2^-59).
-// The result can come out as -1e-17 instead of +0 when u is one ulp below 1; callers take |.|.
-template <class Tab> MCB_FN double neg2log_unit(double u, const Tab &T)
+// The scale k rides on the constants of the last two FMAs and on the job's exponent table S (LogScale64, filled
+// with k ln 2), so e.g. b^2 (-2 ln u) -- the squared radius of a Box-Muller pair already multiplied by a diffusion
+// scale b -- costs the same 9 fp64 instructions as -2 ln u (k = -2).
+// With a 52-bit u one ulp below 1 the result can come out as -1e-17 instead of +0; the kernels' 44-bit uniforms
+// cannot get there (device_math.cuh).
+template <class Tab> MCB_FN double scaled_log_unit(double u, const Tab &T, double k, const LogScale64 &S)
 {
     const int hi = hi_word(u);
-    const int idx = (hi >> 12) & 0xff;
-    const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(u));
-    // exponent as a double without a conversion instruction: 2^52 + biased exponent, minus (2^52 + 1023)
-    const double e = make_double(0x43300000, (int)((unsigned)hi >> 20)) - MCB_K(Tab, log_magic, 4503599627371519.0);
+    const int ebits = hi & 0x7ff00000;
     double c, l;
-    T.log_entry(idx, c, l);
-    const double r = fma_(m, c, -1.0);
-    double q = fma_(r, MCB_K(Tab, log_c6, -1.0 / 6.0), MCB_K(Tab, log_c5, 0.2));
+    T.log_entry(hi, c, l);
+    const double r = fma_(u, make_double(hi_word(c) - ebits, lo_word(c)), -1.0);
+    double q = fma_(r, -1.0 / 6.0, 0.2);
     q = fma_(r, q, -0.25);
-    q = fma_(r, q, MCB_K(Tab, log_c3, 1.0 / 3.0));
+    q = fma_(r, q, 1.0 / 3.0);
     q = fma_(r, q, -0.5);
     const double p = fma_(r * r, q, r);                    // log1p(r)
-    // -2 (e ln2 + l) + 1e-300: the tiny offset (free: it rides in an FMA) keeps the result away from
-    // an exact 0 at u == 1, so the square root below needs no zero guard
-    const double t = fma_(e, MCB_K(Tab, neg2ln2, -2.0 * 0x1.62e42fefa39efp-1), fma_(l, -2.0, MCB_K(Tab, tiny, 1e-300)));
-    return fma_(p, -2.0, t);
+    return fma_(p, k, fma_(l, k, S.entry(ebits)));
 }
-
-// k * ln(u) for a caller-chosen k (k_ln2 = k ln 2): the scale rides on the three constants of the final FMAs, so
-// e.g. b^2 (-2 ln u) -- the squared radius of a Box-Muller pair already multiplied by a diffusion scale b --
-// costs the same 12 instructions as -2 ln u.  neg2log_unit(u) == scaled_log_unit(u, -2, -2 ln 2).
-template <class Tab> MCB_FN double scaled_log_unit(double u, const Tab &T, double k, double k_ln2)
-{
-    const int hi = hi_word(u);
-    const int idx = (hi >> 12) & 0xff;
-    const double m = make_double((hi & 0x000fffff) | 0x3ff00000, lo_word(u));
-    const double e = make_double(0x43300000, (int)((unsigned)hi >> 20)) - MCB_K(Tab, log_magic, 4503599627371519.0);
-    double c, l;
-    T.log_entry(idx, c, l);
-    const double r = fma_(m, c, -1.0);
-    double q = fma_(r, MCB_K(Tab, log_c6, -1.0 / 6.0), MCB_K(Tab, log_c5, 0.2));
-    q = fma_(r, q, -0.25);
-    q = fma_(r, q, MCB_K(Tab, log_c3, 1.0 / 3.0));
-    q = fma_(r, q, -0.5);
-    const double p = fma_(r * r, q, r);                    // log1p(r)
-    const double t = fma_(e, k_ln2, fma_(l, k, MCB_K(Tab, tiny, 1e-300)));
-    return fma_(p, k, t);
-}
+// -2 ln(u): S filled with -2 ln 2
+template <class Tab> MCB_FN double neg2log_unit(double u, const Tab &T, const LogScale64 &S) { return scaled_log_unit(u, T, -2.0, S); }
 
 // ---- sqrt(x), x > 0 finite and normal ------------------------------------------------------------
 // y ~ 1/sqrt(x) to 2^-22 (MUFU.RSQ64H); g = x y, h = y/2.
@@ -299,26 +323,44 @@ MCB_FN void sincos_turn(uint32_t k_hi, uint32_t k_lo, double &cs, double &sn)
 }
 
 // ---- e^x -----------------------------------------------------------------------------------------
-// n = rint(x 256/ln2) (magic-number add), r = x - n ln2/256 (Cody-Waite, |r| <= ln2/512),
-// e^x = 2^(n>>8) * T[n & 255] * (1 + r + r^2/2 + r^3/6 + r^4/24).  The power of two is added to the
-// exponent field as an integer, so the argument must satisfy |x| <= 700: the host validates every
-// job's reachable exponent range (engine.cu: make_*_job) and the CVA kernel floors -d^2/2 at -700.
-template <class Tab> MCB_FN double exp_tab(double x, const Tab &T)
+// exp_units(y) = 2^(y/256) = e^(y ln2/256): the argument in units of the table step.  n = rint(y) by a magic-number
+// add, r = y - n EXACTLY (|r| <= 1/2), 2^(n/256) from the table with the power of two added to its exponent field
+// (bias_exp_entry), e^(r ln2/256) - 1 by its degree-4 Taylor polynomial with the powers of ln2/256 folded into the
+// coefficients (truncation (ln2/512)^5/120 < 2^-54).  8 fp64 instructions and no Cody-Waite reduction: a caller
+// whose exponent is a sum of products (a + b z; a GBM step) scales its constants by 256/ln2 on the host and pays
+// nothing for it.  The relative rounding error of y is the same 2^-53 that the natural-units argument would carry,
+// so nothing is lost.  |y| <= 700 * 256/ln2: the host validates every job's reachable exponent range
+// (engine.cu: make_*_job) and the CVA kernel floors its density exponent.
+template <class Tab> MCB_FN double exp_units(double y, const Tab &T)
 {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52 (an immediate: low word zero)
-    const double t = fma_(x, MCB_K(Tab, exp_scale, 0x1.71547652b82fep+8), magic);
+    const double t = y + magic;
+    const int n = lo_word(t);
+    const double r = y - (t - magic);
+    const double tj = T.exp_entry(n);
+    const double ts = make_double(hi_word(tj) + (int)((uint32_t)n << 12), lo_word(tj));   // 2^(n/256)
+    double p = fma_(r, 0x1.3b2ab6fba4e77p-39 /* h^4/24 */, 0x1.c6b08d704a0c0p-29 /* h^3/6 */);
+    p = fma_(r, p, 0x1.ebfbdff82c58fp-19 /* h^2/2 */);
+    p = fma_(r, p, 0x1.62e42fefa39efp-9 /* h = ln2/256 */);
+    return fma_(ts * r, p, ts);
+}
+
+// e^x for an argument in natural units: the same with a Cody-Waite reduction in front (10 fp64 instructions).
+// |x| <= 700.
+template <class Tab> MCB_FN double exp_tab(double x, const Tab &T)
+{
+    const double magic = 6755399441055744.0;
+    const double t = fma_(x, 0x1.71547652b82fep+8, magic);
     const int n = lo_word(t);
     const double nd = t - magic;
-    double r = fma_(nd, MCB_K(Tab, exp_ln2_hi, -0x1.62e42fee00000p-9), x);
-    r = fma_(nd, MCB_K(Tab, exp_ln2_lo, -0x1.a39ef35793c76p-41), r);
-    const double tj = T.exp_entry(n & 255);
-    double p = fma_(r, MCB_K(Tab, exp_c4, 1.0 / 24.0), MCB_K(Tab, exp_c3, 1.0 / 6.0));
+    double r = fma_(nd, -0x1.62e42fee00000p-9, x);
+    r = fma_(nd, -0x1.a39ef35793c76p-41, r);
+    const double tj = T.exp_entry(n);
+    const double ts = make_double(hi_word(tj) + (int)((uint32_t)n << 12), lo_word(tj));
+    double p = fma_(r, 1.0 / 24.0, 1.0 / 6.0);
     p = fma_(r, p, 0.5);
     p = fma_(r * r, p, r);          // e^r - 1
-    const double v = fma_(tj, p, tj);
-    // (the exponent insertion as mask + IMAD -- one instruction fewer than shift, mask, add -- was measured: European
-    // call 2 % slower, basket-10 1.3 % faster, CVA 1 % slower, profiles/r01p_ab_experiments.txt; not used)
-    return make_double(hi_word(v) + ((n >> 8) << 20), lo_word(v));
+    return fma_(ts, p, ts);
 }
 
 // ---- max(x, 0) on the integer pipe: clear every bit when the sign bit is set ----------------------

@@ -4,7 +4,8 @@
 // :133-177).  One draw unit = one path; draw block j of the path's sub-stream gives normals
 // kNpb * j .. kNpb * j + kNpb - 1 (kNpb = 6 in fp32, 4 in fp64).
 //   x_i    = a_i + sum_j F_ij z_j      F_ij = v_i sqrt(T) L_ij,  a_i = (r - v_i^2/2) T + v_i sqrt(T) d_i
-//   payoff = max(sum_i m_i e^{x_i} - K, 0),  m_i = w_i s_i      (fp32: x in log2 units, 2^x by MUFU.EX2)
+//   payoff = max(sum_i m_i e^{x_i} - K, 0),  m_i = w_i s_i      (x in the units of exp_scaled: log2 units for MUFU.EX2
+//                                                                in fp32, units of ln2/256 for exp_units in fp64)
 // The mat-vec is a column sweep kept in registers: normal j is produced, applied to the N - j
 // accumulators at or below the diagonal and discarded, so N accumulators + one normal are live
 // and every factor entry reaches the FMA pipe as a constant-bank operand.  The reference indexes
@@ -152,12 +153,19 @@ struct SharedFactor64 : SharedTables64Rep {
             factor[i] = src[i];
     }
 };
-// Wide fp64 baskets (two-pass sweep, see Basket::eval_two_pass): the plain math tables plus one slot per thread and
-// sub-block for each normal of the first half ([normal][thread]: consecutive threads, conflict-free 8-byte accesses).
-// 38 KB + 2 x 64 KB; the replicated tables (96 KB) would not fit next to the slots.
+// Wide fp64 baskets (two-pass sweep, see Basket::eval_two_pass): the plain math tables with the coarse angle table
+// next to them, plus one slot per thread and sub-block for each normal of the first half ([normal][thread]: consecutive
+// threads, conflict-free 8-byte accesses).  10 KB + 64 KB + 2 x 64 KB; the replicated tables (160 KB) would not fit
+// next to the slots.
 template <int kHalf>
-struct SharedTwoPass64 : SharedTables64 {
+struct SharedTwoPass64 {
+    Tables64Wide t;
     double stash[2][kHalf][kThreads];  // [sub-block]: Basket::kSubBlocks == 2 for the two-pass kernel (static_assert there)
+    __device__ __forceinline__ void load()
+    {
+        for (int i = threadIdx.x; i < 4096; i += blockDim.x)
+            t.fill_wide(i);
+    }
 };
 // xa, xb += {2 consecutive factor entries at smem address base + kByteOffset} * z
 template <int kByteOffset>
@@ -225,12 +233,17 @@ struct Basket {
         kSharedFactor, SharedFactor<(kSharedFactor ? Table::kFactor : 1)>,
         std::conditional_t<kSharedFactor64, SharedFactor64<(kSharedFactor64 ? Table::kFactor : 1)>,
                            std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>>>>;
-    template <class Sh> static __device__ __forceinline__ Real grow(Real x, const Sh &sh)
+    using JobState = typename JobStateFor<Real>::type;   // fp64: the exponent table of -2 ln u
+    static constexpr bool kClampAtZero = sizeof(Real) == 8;   // fp64: add_value clamps the payoff (device_common.cuh)
+    static __device__ __forceinline__ void prepare(const Params &, JobState &job, int tid) { prepare_polar(polar_scale<Real>(1.0), job, tid); }
+    // exponents are kept in the units of exp_scaled (fill_table): log2 units for fp32, units of ln2/256 for fp64
+    template <class Sh> static __device__ __forceinline__ Real grow(Real x, const Sh &sh) { return exp_scaled(x, sh); }
+    static __device__ __forceinline__ Real clamp(Real payoff)
     {
-        if constexpr (sizeof(Real) == 4)
-            return mufu_ex2(x);
+        if constexpr (kClampAtZero)
+            return payoff;
         else
-            return exp_tab(x, sh.t);
+            return positive_part(payoff);
     }
     static constexpr int kBlocks = (N + kNpb - 1) / kNpb;
     static constexpr int kFactorBase = 0;
@@ -305,12 +318,12 @@ struct Basket {
     // draw block JB: one Philox block -> kNpb normals -> kNpb columns
     template <int JB>
     static __device__ __forceinline__ void draw_block(const Params &P, uint32_t path_lo, uint32_t path_hi, State &st,
-                                                      const Shared &sh)
+                                                      const Shared &sh, const JobState &job)
     {
         uint32_t w[4];
         philox4x32_10(path_lo, path_hi, (uint32_t)JB, kTagBasket, P.keys, w);
         Real z[kNpb];
-        normals_from_words(w, z, sh);
+        normals_from_words(w, z, sh, job);
         columns<JB>(st, z, sh, std::make_integer_sequence<int, kNpb>{});
     }
     template <int JB, int... kQ>
@@ -321,9 +334,9 @@ struct Basket {
     }
     template <int... kJB>
     static __device__ __forceinline__ void sweep(const Params &P, uint32_t path_lo, uint32_t path_hi, State &st,
-                                                 const Shared &sh, std::integer_sequence<int, kJB...>)
+                                                 const Shared &sh, const JobState &job, std::integer_sequence<int, kJB...>)
     {
-        (draw_block<kJB>(P, path_lo, path_hi, st, sh), ...);
+        (draw_block<kJB>(P, path_lo, path_hi, st, sh, job), ...);
     }
     template <int... kI>
     static __device__ __forceinline__ void init(State &st, std::integer_sequence<int, kI...>)
@@ -346,7 +359,7 @@ struct Basket {
     {
         Real sum = -table_entry<Real, kKBase>();
         ((sum = fma(table_entry<Real, kMBase + kI * (int)sizeof(Real)>(), grow(exponent<kI>(st), sh), sum)), ...);
-        return positive_part(sum);
+        return clamp(sum);
     }
     // ---- two-pass sweep (kTwoPass) ----
     // rows kRow0 + kRow... of column J into the accumulators x[row - kOff]
@@ -360,37 +373,39 @@ struct Basket {
     // draw block JB of the first half: normals 4 JB .. 4 JB + 3 -> their slots and the rows J .. kHalf-1
     template <int JB, int... kQ>
     static __device__ __forceinline__ void first_half_block(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&x)[kHalf],
-                                                            const Shared &sh, Real (*slots)[kThreads], std::integer_sequence<int, kQ...>)
+                                                            const Shared &sh, const JobState &job, Real (*slots)[kThreads],
+                                                            std::integer_sequence<int, kQ...>)
     {
         uint32_t w[4];
         philox4x32_10(path_lo, path_hi, (uint32_t)JB, kTagBasket, P.keys, w);
         Real z[kNpb];
-        normals_from_words(w, z, sh);
+        normals_from_words(w, z, sh, job);
         ((slots[JB * kNpb + kQ][0] = z[kQ]), ...);
         (column_rows<JB * kNpb + kQ, JB * kNpb + kQ, 0>(x, z[kQ], std::make_integer_sequence<int, kHalf - (JB * kNpb + kQ)>{}), ...);
     }
     // draw block JB of the second half: rows J .. N-1 (all in the upper half)
     template <int JB, int... kQ>
     static __device__ __forceinline__ void second_half_block(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&x)[kHalf],
-                                                             const Shared &sh, std::integer_sequence<int, kQ...>)
+                                                             const Shared &sh, const JobState &job, std::integer_sequence<int, kQ...>)
     {
         uint32_t w[4];
         philox4x32_10(path_lo, path_hi, (uint32_t)JB, kTagBasket, P.keys, w);
         Real z[kNpb];
-        normals_from_words(w, z, sh);
+        normals_from_words(w, z, sh, job);
         (column_rows<JB * kNpb + kQ, JB * kNpb + kQ, kHalf>(x, z[kQ], std::make_integer_sequence<int, N - (JB * kNpb + kQ)>{}), ...);
     }
     template <int... kJB>
     static __device__ __forceinline__ void first_half(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&x)[kHalf],
-                                                      const Shared &sh, Real (*slots)[kThreads], std::integer_sequence<int, kJB...>)
+                                                      const Shared &sh, const JobState &job, Real (*slots)[kThreads],
+                                                      std::integer_sequence<int, kJB...>)
     {
-        (first_half_block<kJB>(P, path_lo, path_hi, x, sh, slots, std::make_integer_sequence<int, kNpb>{}), ...);
+        (first_half_block<kJB>(P, path_lo, path_hi, x, sh, job, slots, std::make_integer_sequence<int, kNpb>{}), ...);
     }
     template <int... kJB>
     static __device__ __forceinline__ void second_half(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&x)[kHalf],
-                                                       const Shared &sh, std::integer_sequence<int, kJB...>)
+                                                       const Shared &sh, const JobState &job, std::integer_sequence<int, kJB...>)
     {
-        (second_half_block<kHalf / kNpb + kJB>(P, path_lo, path_hi, x, sh, std::make_integer_sequence<int, kNpb>{}), ...);
+        (second_half_block<kHalf / kNpb + kJB>(P, path_lo, path_hi, x, sh, job, std::make_integer_sequence<int, kNpb>{}), ...);
     }
     // the dense block: parked normal J times rows kHalf .. N-1
     template <int... kJ>
@@ -410,7 +425,7 @@ struct Basket {
         return sum;
     }
     static __device__ __forceinline__ void eval_two_pass(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
-                                                         const Shared &sh)
+                                                         const Shared &sh, const JobState &job)
     {
         static_assert(!kTwoPass || (kHalf % kNpb == 0 && N % kNpb == 0), "halves must fall on draw-block boundaries");
         static_assert(!kTwoPass || kSubBlocks == 2, "SharedTwoPass64 holds the slots of two sub-blocks");
@@ -420,23 +435,23 @@ struct Basket {
         using Half = std::make_integer_sequence<int, kHalf>;
         Real x[kHalf];
         half_init<0>(x, Half{});
-        first_half(P, path_lo, path_hi, x, sh, slots, std::make_integer_sequence<int, kHalf / kNpb>{});
+        first_half(P, path_lo, path_hi, x, sh, job, slots, std::make_integer_sequence<int, kHalf / kNpb>{});
         Real sum = half_value<0>(x, -table_entry<Real, kKBase>(), sh, Half{});
         half_init<kHalf>(x, Half{});
         parked_columns(x, slots, Half{});
-        second_half(P, path_lo, path_hi, x, sh, std::make_integer_sequence<int, (N - kHalf) / kNpb>{});
-        v[0] = positive_part(half_value<kHalf>(x, sum, sh, Half{}));
+        second_half(P, path_lo, path_hi, x, sh, job, std::make_integer_sequence<int, (N - kHalf) / kNpb>{});
+        v[0] = clamp(half_value<kHalf>(x, sum, sh, Half{}));
     }
     static __device__ __forceinline__ void eval(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
-                                                const Shared &sh)
+                                                const Shared &sh, const JobState &job)
     {
         if constexpr (kTwoPass) {
-            eval_two_pass(P, path_lo, path_hi, v, sh);
+            eval_two_pass(P, path_lo, path_hi, v, sh, job);
             return;
         }
         State st;
         init(st, std::make_integer_sequence<int, (kPaired ? N / 2 : N)>{});
-        sweep(P, path_lo, path_hi, st, sh, std::make_integer_sequence<int, kBlocks>{});
+        sweep(P, path_lo, path_hi, st, sh, job, std::make_integer_sequence<int, kBlocks>{});
         v[0] = payoff(st, sh, std::make_integer_sequence<int, N>{});
     }
 };
@@ -453,7 +468,7 @@ template <typename Real, int N, bool kFull>
 static void fill_table(const BasketJob &job, BasketTable<Real, N, kFull> &T)
 {
     using Table = BasketTable<Real, N, kFull>;
-    const double unit = sizeof(Real) == 4 ? 1.4426950408889634074 : 1.0;  // log2(e) for the MUFU.EX2 path
+    const double unit = ExpUnit<Real>::value;  // exponents in the units of exp_scaled: 1/ln2 (MUFU.EX2) or 256/ln2 (exp_units)
     for (int i = 0; i < Table::kFactor; i++)
         T.factor[i] = 0;
     for (int col = 0; col < N; col++)

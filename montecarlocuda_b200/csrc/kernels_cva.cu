@@ -2,18 +2,24 @@
 //
 // Replaces geomBrownian + cnd + device_bsCall + cvaCallOptMC (DP/MonteCarloKernel.cu:104-129,
 // :222-283).  One draw unit = one path; exposure date j uses normal j of the path's sub-stream.
-// The state is the log-moneyness y = ln(S/K).  Per kept date j (host-built table, engine.cu):
+// The state is the log-moneyness y = ln(S/K), and everything is priced per unit of strike.  Per kept date j
+// (host-built table, engine.cu):
 //   y  += mu_dt + sig_dt z                      exact GBM step
-//   s   = K e^y
+//   s   = e^y                                   = S / K
 //   d1  = y inv_j + c1_j,  d2 = d1 - sig_j      inv_j = 1/(v sqrt(tau_j)), c1_j = (r + v^2/2) tau_j inv_j
-//   A   = s phi(d1) = K/sqrt(2 pi) e^{y - d1^2/2}  one exponential; kd_j phi(d2) = A as well (kd_j = K e^{-r tau_j})
-//   q_i = cnd-tail(|d_i|) / phi(d_i)             Hastings polynomial in 1 / (1 + 0.2316419 |d_i|), like the reference
+//   A   = e^{y - d1^2/2}                         one exponential: sqrt(2 pi) s phi(d1), and sqrt(2 pi) kd_j phi(d2) as
+//                                               well (kd_j = e^{-r tau_j})
+//   q_i = cnd-tail(|d_i|) / (sqrt(2 pi) phi(d_i))   Hastings polynomial in 1 / (1 + 0.2316419 |d_i|), like the
+//                                               reference, with 1/sqrt(2 pi) folded into its coefficients
 //   ee  = s cnd(d1) - kd_j cnd(d2)
 //       = s [d1 > 0] - kd_j [d2 > 0] - A (sgn(d1) q1 - sgn(d2) q2)
-//   cva += w_j ee                               w_j = LGD (e^{-lambda t_{j-1}} - e^{-lambda t_j})
+//   cva += w_j ee                               w_j = K LGD (e^{-lambda t_{j-1}} - e^{-lambda t_j})
 // so a path-step costs one normal, two exponentials and two reciprocals; the reference spends six
-// exponentials, a log, three square roots and four divisions on it.  Dates the reference drops
-// (remaining time rounded below zero) are simply absent from the table.
+// exponentials, a log, three square roots and four divisions on it.  y is carried in the units the exponential
+// is cheapest in (exp_scaled: log2 units for fp32, units of ln2/256 for fp64; the table's inv_j and the -1/2 of the
+// density exponent absorb the factor), so neither exponential has an argument reduction to pay for and neither
+// result is multiplied by anything.  Dates the reference drops (remaining time rounded below zero)
+// are simply absent from the table.
 #include <type_traits>
 #include <vector>
 
@@ -26,9 +32,6 @@
 // (profiles/r01p_ab_experiments.txt; tools/build_variant.sh builds the other one for A/B timing)
 #define MCB_CVA_SUBBLOCKS 2
 #endif
-#ifndef MCB_CVA_BANK
-#define MCB_CVA_BANK 0  // fp64 math constants as constant-bank operands (1) or literals (0): at 128 registers literals win, 16.92 vs 17.01 ms
-#endif
 
 namespace mcb {
 
@@ -40,27 +43,18 @@ struct alignas(16) CvaDate {  // three 16-byte constant loads per date
 __constant__ __align__(16) unsigned char c_cva_table[kCvaMaxDates * sizeof(CvaDate<double>)];
 static TableLock g_cva_lock;
 
-// q(d) = cnd-tail(|d|) / phi(d) = k polynomial(k), k = 1 / (1 + 0.2316419 |d|)
-// (Abramowitz-Stegun 26.2.17, the constants of DP/MonteCarloKernel.cu:111-116)
-template <typename Real, bool kBank = false>
+// q(d) = cnd-tail(|d|) / (sqrt(2 pi) phi(d)) = k polynomial(k), k = 1 / (1 + 0.2316419 |d|)
+// (Abramowitz-Stegun 26.2.17, the constants of DP/MonteCarloKernel.cu:111-116 times 1/sqrt(2 pi))
+template <typename Real>
 __device__ __forceinline__ Real hastings_ratio(Real d)
 {
-    if constexpr (kBank) {
-        const MathConsts64 &K = kMathConsts64;  // constant-bank operands instead of re-materialised immediates
-        const double k = rcp_real(fma(K.hast_k, fabs(d), 1.0));
-        double poly = fma(k, K.hast_a5, K.hast_a4);
-        poly = fma(k, poly, K.hast_a3);
-        poly = fma(k, poly, K.hast_a2);
-        poly = fma(k, poly, K.hast_a1);
-        return k * poly;
-    } else {
-        const Real k = rcp_real(fma((Real)0.2316419, fabs(d), (Real)1.0));
-        Real poly = fma(k, (Real)1.330274429, (Real)-1.821255978);
-        poly = fma(k, poly, (Real)1.781477937);
-        poly = fma(k, poly, (Real)-0.356563782);
-        poly = fma(k, poly, (Real)0.31938153);
-        return k * poly;
-    }
+    constexpr double c = 0.39894228040143267793994605993438;
+    const Real k = rcp_real(fma((Real)0.2316419, fabs(d), (Real)1.0));
+    Real poly = fma(k, (Real)(1.330274429 * c), (Real)(-1.821255978 * c));
+    poly = fma(k, poly, (Real)(1.781477937 * c));
+    poly = fma(k, poly, (Real)(-0.356563782 * c));
+    poly = fma(k, poly, (Real)(0.31938153 * c));
+    return k * poly;
 }
 
 // sgn(d) q for q > 0 and x [d > 0], by the sign bit of d on the integer pipe (the fp64 comparisons are
@@ -74,25 +68,27 @@ __device__ __forceinline__ float with_sign_of(float q, float d)
 {
     return __int_as_float(__float_as_int(q) ^ (__float_as_int(d) & (int)0x80000000));
 }
+// (fp64: only the HIGH word is cleared -- what is left is below 2^-1042, i.e. nothing next to any term it meets here,
+// and costs two integer instructions instead of three)
 __device__ __forceinline__ double keep_if_positive(double x, double d)
 {
-    const int keep = ~(__double2hiint(d) >> 31);
-    return __hiloint2double(__double2hiint(x) & keep, __double2loint(x) & keep);
+    return __hiloint2double(__double2hiint(x) & ~(__double2hiint(d) >> 31), __double2loint(x));
 }
 __device__ __forceinline__ float keep_if_positive(float x, float d)
 {
     return __int_as_float(__float_as_int(x) & ~(__float_as_int(d) >> 31));
 }
 
-// max(a, -700) without touching the fp64 pipe: negative doubles order like their high words taken as
-// unsigned integers and every non-negative one lies below them, so one integer min on the high word does
-// it (-inf included).
-__device__ __forceinline__ double floor_at_minus_700(double a)
+// max(a, -258048) -- e^-698.7 in units of ln2/256 -- without touching the fp64 pipe: negative doubles order like
+// their high words taken as unsigned integers and every non-negative one lies below them, so one integer min on the
+// high word does it (-inf and NaN included).  The low word stays as it is: a floored value lies within a quarter of
+// -258048, still inside the exponential's range and still e^x = 0 for every purpose.
+__device__ __forceinline__ double floor_exponent(double a)
 {
-    const unsigned hi = min((unsigned)__double2hiint(a), 0xC085E000u);  // high word of -700.0
-    return __hiloint2double((int)hi, hi == 0xC085E000u ? 0 : __double2loint(a));
+    constexpr unsigned kFloorHi = 0xC10F8000u;  // high word of -258048.0
+    return __hiloint2double((int)min((unsigned)__double2hiint(a), kFloorHi), __double2loint(a));
 }
-__device__ __forceinline__ float floor_at_minus_700(float a) { return a; }  // MUFU.EX2(-inf) = 0
+__device__ __forceinline__ float floor_exponent(float a) { return a; }  // MUFU.EX2(-inf) = 0
 
 template <typename RealT, bool kAccumLayout = false>
 struct Cva {
@@ -104,34 +100,34 @@ struct Cva {
     static constexpr int kNpb = NormalsPerBlock<RealT>::value;
     struct Params {
         PhiloxKeys keys;
-        Real y0, mu_dt, k, k_pdf;  // k_pdf = K / sqrt(2 pi)
-        PolarScale<Real> scale;  // of sig_dt = v sqrt(dt), folded under the Box-Muller square root
+        Real y0, mu_dt;          // ln(S0/K) and the drift of a step, in the units of exp_scaled
+        Real half_unit;          // -1/2 of that unit: the density exponent y - d1^2/2
+        PolarScale<Real> scale;  // of sig_dt = v sqrt(dt) (same units), folded under the Box-Muller square root
         int n_dates;  // kept dates
         int first_date;  // of this job in the device table (0 unless the launch carries several jobs)
     };
-    // fp64 pricing kernel: replicated tables; math constants from the constant bank only when asked (MCB_CVA_BANK: the
-    // right choice under the 80-register cap of 3 sub-blocks, see device_math64.cuh)
-    static constexpr bool kBank = kAccumLayout && sizeof(RealT) == 8 && MCB_CVA_BANK;
-    using Shared = std::conditional_t<kBank, SharedTables64RepBank,
-                                      std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>>;
+    using Shared = std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>;
+    using JobState = typename JobStateFor<Real>::type;
+    static constexpr bool kClampAtZero = false;
+    static __device__ __forceinline__ void prepare(const Params &P, JobState &job, int tid) { prepare_polar(P.scale, job, tid); }
     // one exposure date; the diffusion sig_dt z arrives as (sig_dt r) * (cos or sin) and folds into the step's FMA
     static __device__ __forceinline__ void step(const Params &P, const CvaDate<Real> &D, Real sr, Real trig, Real &y,
                                                 Real &cva, const Shared &sh)
     {
         y = fma(sr, trig, y + P.mu_dt);
-        const Real s = P.k * exp_real(y, sh);
+        const Real s = exp_scaled(y, sh);
         const Real d1 = fma(y, D.inv, D.c1);
         const Real d2 = d1 - D.sig;
-        // s phi(d1) = kd phi(d2) = K / sqrt(2 pi) e^{y - d1^2/2}.  The exponent can be -1e14 (a date a few ulps before
-        // maturity) or -inf (exact grid, tau = 0): floor it where e^x is already 0 for every purpose, so the
+        // sqrt(2 pi) s phi(d1) = sqrt(2 pi) kd phi(d2) = e^{y - d1^2/2}.  The exponent can be -1e14 (a date a few ulps
+        // before maturity) or -inf (exact grid, tau = 0): floor it where e^x is already 0 for every purpose, so the
         // table-driven exp stays in range
-        const Real a = P.k_pdf * exp_real(floor_at_minus_700(fma((Real)-0.5 * d1, d1, y)), sh);
-        const Real tails = with_sign_of(hastings_ratio<Real, kBank>(d1), d1) - with_sign_of(hastings_ratio<Real, kBank>(d2), d2);
+        const Real a = exp_scaled(floor_exponent(fma(P.half_unit * d1, d1, y)), sh);
+        const Real tails = with_sign_of(hastings_ratio<Real>(d1), d1) - with_sign_of(hastings_ratio<Real>(d2), d2);
         const Real ee = fma(-a, tails, keep_if_positive(s, d1) - keep_if_positive(D.kd, d2));
         cva = fma(D.w, ee, cva);
     }
     static __device__ __forceinline__ void eval(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
-                                                const Shared &sh)
+                                                const Shared &sh, const JobState &job)
     {
         const CvaDate<Real> *dates = reinterpret_cast<const CvaDate<Real> *>(c_cva_table) + P.first_date;
         Real y = P.y0, cva = 0;
@@ -143,7 +139,7 @@ struct Cva {
             uint32_t w[4];
             philox4x32_10(path_lo, path_hi, (uint32_t)jb, kTagCva, P.keys, w);
             Real sr[kNpb / 2], cs[kNpb / 2], sn[kNpb / 2];
-            polar_from_words<true>(w, sr, cs, sn, sh, P.scale);
+            polar_from_words<true>(w, sr, cs, sn, sh, P.scale, job);
 #pragma unroll
             for (int q = 0; q < kNpb; q++)
                 step(P, dates[jb * kNpb + q], sr[q / 2], (q & 1) ? sn[q / 2] : cs[q / 2], y, cva, sh);
@@ -152,7 +148,7 @@ struct Cva {
             uint32_t w[4];
             philox4x32_10(path_lo, path_hi, (uint32_t)n_whole, kTagCva, P.keys, w);
             Real sr[kNpb / 2], cs[kNpb / 2], sn[kNpb / 2];
-            polar_from_words<true>(w, sr, cs, sn, sh, P.scale);
+            polar_from_words<true>(w, sr, cs, sn, sh, P.scale, job);
 #pragma unroll
             for (int q = 0; q < kNpb - 1; q++) {
                 const int j = n_whole * kNpb + q;
@@ -169,12 +165,12 @@ static typename W::Params narrow(const CvaJob &job)
 {
     using Real = typename W::Real;
     typename W::Params p;
+    constexpr double unit = ExpUnit<Real>::value;
     p.keys = job.keys;
-    p.y0 = (Real)job.y0;
-    p.mu_dt = (Real)job.mu_dt;
-    p.scale = polar_scale<Real>(job.sig_dt);
-    p.k = (Real)job.k;
-    p.k_pdf = (Real)(job.k * 0.39894228040143267793994605993438);
+    p.y0 = (Real)(job.y0 * unit);
+    p.mu_dt = (Real)(job.mu_dt * unit);
+    p.half_unit = (Real)(-0.5 * unit);
+    p.scale = polar_scale<Real>(job.sig_dt * unit);
     p.n_dates = job.n_dates;
     p.first_date = 0;
     return p;
@@ -204,7 +200,9 @@ static bool stage_dates(const CvaJob &job, std::vector<CvaDate<Real>> &staging)
         return false;
     for (int j = 0; j < job.n_dates; j++) {
         const CvaDateHost &h = job.dates[j];
-        staging.push_back(CvaDate<Real>{(Real)h.w, (Real)h.inv, (Real)h.c1, (Real)h.sig, (Real)h.kd, (Real)0});
+        // per unit of strike, slope per unit of the kernel's y (see the header of this file)
+        staging.push_back(CvaDate<Real>{(Real)(h.w * job.k), (Real)(h.inv / ExpUnit<Real>::value), (Real)h.c1, (Real)h.sig,
+                                        (Real)(h.kd / job.k), (Real)0});
     }
     return true;
 }

@@ -25,14 +25,16 @@ __global__ void debug_normals_kernel(unsigned long long n, const uint32_t *__res
                                      const __grid_constant__ PhiloxKeys keys, Real *__restrict__ out)
 {
     __shared__ typename SharedFor<Real>::type sh;
+    __shared__ typename JobStateFor<Real>::type job;
     sh.load();
+    prepare_polar(polar_scale<Real>(1.0), job, (int)threadIdx.x);
     __syncthreads();
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t w[4];
         philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], keys, w);
         Real z[kPerBlock];
-        normals_from_words(w, z, sh);
+        normals_from_words(w, z, sh, job);
 #pragma unroll
         for (int q = 0; q < kPerBlock; q++)
             out[kPerBlock * i + q] = z[q];
@@ -77,19 +79,23 @@ debug_reduce_kernel(const double *__restrict__ values, unsigned long long n_vali
 
 // The fp64 special functions on their own: fn 0 = -2 ln(u), 1 = sqrt, 2 = 1/x, 3 = e^x,
 // 4 = cos/sin of 2 pi k / 2^52 (input reinterpreted as the 52-bit integer k; two outputs),
-// 5 = cos/sin of 2 pi k / 2^20 from the two-level table (k = low word of the input).
+// 5 = cos/sin of 2 pi k / 2^20 from the two-level table (k = low word of the input), 6 = sqrt (short iteration),
+// 7 = 2^(y/256) (exp_units).
 __global__ void debug_math64_kernel(int fn, unsigned long long n, const double *__restrict__ in,
                                     double *__restrict__ out)
 {
     __shared__ SharedTables64 sh;
+    __shared__ LogScale64 job;
     sh.load();
+    prepare_polar(polar_scale<double>(1.0), job, (int)threadIdx.x);
     __syncthreads();
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const double x = in[i];
         double a = 0, b = 0;
         switch (fn) {
-            case 0: a = neg2log_unit(x, sh.t); break;
+            case 0: a = neg2log_unit(x, sh.t, job); break;
+            case 7: a = exp_units(x, sh.t); break;
             case 1: a = sqrt_pos(x); break;
             case 6: a = sqrt_pos<true>(x); break;
             case 2: a = rcp_newton(x); break;

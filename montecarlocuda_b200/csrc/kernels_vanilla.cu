@@ -3,9 +3,9 @@
 //
 // Replaces callPayoff + vanillaOptMonteCarlo (DP/MonteCarloKernel.cu:67-71, :179-220).
 // One draw unit = one Philox block = 6 (fp32) or 4 (fp64) consecutive paths:
-//   fp32: payoff = max(2^(a + b z) - K, 0),  a = log2(S0) + (r - v^2/2) T log2(e),  b = v sqrt(T) log2(e)
-//   fp64: payoff = max(e^(a + b z) - K, 0),  a = ln(S0) + (r - v^2/2) T,            b = v sqrt(T)
-// so a path costs one FMA and one exponential after its normal.
+//   payoff = max(e^(a + b z) - K, 0),  a = ln(S0) + (r - v^2/2) T,  b = v sqrt(T)
+// with a and b scaled on the host into the units the exponential is cheapest in (fp32: log2 units for MUFU.EX2; fp64:
+// units of ln2/256 for the table-driven exp_units), so a path costs one FMA and one exponential after its normal.
 #include "launch.h"
 #include "workload_vanilla.cuh"
 
@@ -19,9 +19,9 @@ static typename W::Params narrow(const VanillaJob &job)
     using Real = typename W::Real;
     typename W::Params p;
     p.keys = job.keys;
-    p.a = (Real)job.a;
+    p.a = (Real)(job.a * ExpUnit<Real>::value);
     p.k = (Real)job.k;
-    p.scale = polar_scale<Real>(job.b);
+    p.scale = polar_scale<Real>(job.b * ExpUnit<Real>::value);
     return p;
 }
 

@@ -41,7 +41,7 @@ inline void fill_batch_header(B &b, const BatchShape &shape, const BatchTarget &
 }
 
 // ---- vanilla (DP/MonteCarloKernel.cu:67-71, :179-220) ----
-// a, b in log2 units for fp32 and natural-log units for fp64 (see kernels_vanilla.cu)
+// a = ln S0 + (r - v^2/2) T, b = v sqrt(T) in natural-log units; the launcher rescales for the kernel (kernels_vanilla.cu)
 struct VanillaJob {
     PhiloxKeys keys;
     double a, b, k;

@@ -10,12 +10,22 @@ namespace mcb {
 
 constexpr uint32_t kVanillaTag = 1u;
 
+#ifndef MCB_VANILLA_SHORT_SQRT
+#define MCB_VANILLA_SHORT_SQRT true   // 5-instruction square root (device_math64.cuh); false: 7 (A/B switch, tools/build_variant.sh)
+#endif
+
 // tuned on B200 (profiles/r01_tune_vanilla.txt): CTAs per SM / unroll of the unit loop
 template <typename Real> struct VanillaTuning;
 template <> struct VanillaTuning<float> { static constexpr int kMinBlocks = 8, kUnroll = 1; };
 // fp64: sub-blocks of 256 threads per CTA around one replicated table set (96 KB).  3 sub-blocks leave 80 registers
 // per thread and the kernel spills (11.5 ms); 2 leave 128 (94 used): 9.70 ms (profiles/r01k_tune_vanilla.txt)
-template <> struct VanillaTuning<double> { static constexpr int kMinBlocks = 2, kUnroll = 1; };
+#ifndef MCB_VANILLA_UNROLL
+#define MCB_VANILLA_UNROLL 1
+#endif
+#ifndef MCB_VANILLA_SUBBLOCKS
+#define MCB_VANILLA_SUBBLOCKS 2
+#endif
+template <> struct VanillaTuning<double> { static constexpr int kMinBlocks = MCB_VANILLA_SUBBLOCKS, kUnroll = MCB_VANILLA_UNROLL; };
 
 // kAccumLayout: instantiated by mc_accumulate_kernel (bank-conflict-free fp64 tables shared by kSubBlocks x 256
 // threads per CTA) rather than by the per-path / instrumentation kernels (plain tables, 256 threads)
@@ -28,21 +38,27 @@ struct Vanilla {
     static constexpr int kSubBlocks = (kAccumLayout && sizeof(RealT) == 8) ? kMinBlocksT : 1;
     static constexpr int kMinBlocks = kSubBlocks > 1 ? 1 : kMinBlocksT;
     static constexpr int kUnroll = kUnrollT;
+    // a and b = v sqrt(T) in the units the exponential is cheapest in (exp_scaled: log2 units for fp32, units of
+    // ln2/256 for fp64); b rides under the Box-Muller square root
     struct Params {
         PhiloxKeys keys;
         Real a, k;
-        PolarScale<Real> scale;  // of b = v sqrt(T) (in the exponent's units), folded under the Box-Muller square root
+        PolarScale<Real> scale;
     };
     using Shared = std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>;
-    template <class Sh> static __device__ __forceinline__ Real grow(Real x, const Sh &sh)
+    using JobState = typename JobStateFor<Real>::type;
+    // fp64: eval returns S_T - K and add_value clamps (sign test + predicated accumulation); fp32: one FMNMX here
+    static constexpr bool kClampAtZero = sizeof(Real) == 8;
+    static __device__ __forceinline__ void prepare(const Params &P, JobState &job, int tid) { prepare_polar(P.scale, job, tid); }
+    static __device__ __forceinline__ Real payoff(Real s_t, Real k)
     {
-        if constexpr (sizeof(Real) == 4)
-            return mufu_ex2(x);
+        if constexpr (kClampAtZero)
+            return s_t - k;
         else
-            return exp_tab(x, sh.t);
+            return positive_part(s_t - k);
     }
     static __device__ __forceinline__ void eval(const Params &P, uint32_t unit_lo, uint32_t unit_hi,
-                                                Real (&v)[kUnitPaths], const Shared &sh)
+                                                Real (&v)[kUnitPaths], const Shared &sh, const JobState &job)
     {
         uint32_t w[4];
         philox4x32_10(unit_lo, unit_hi, 0u, kVanillaTag, P.keys, w);
@@ -50,11 +66,11 @@ struct Vanilla {
         // and one exponential after its pair's (b r, cos, sin)
         constexpr int kPairs = kUnitPaths / 2;
         Real br[kPairs], cs[kPairs], sn[kPairs];
-        polar_from_words(w, br, cs, sn, sh, P.scale);
+        polar_from_words<MCB_VANILLA_SHORT_SQRT>(w, br, cs, sn, sh, P.scale, job);
 #pragma unroll
         for (int i = 0; i < kPairs; i++) {
-            v[2 * i] = positive_part(grow(fma(br[i], cs[i], P.a), sh) - P.k);
-            v[2 * i + 1] = positive_part(grow(fma(br[i], sn[i], P.a), sh) - P.k);
+            v[2 * i] = payoff(exp_scaled(fma(br[i], cs[i], P.a), sh), P.k);
+            v[2 * i + 1] = payoff(exp_scaled(fma(br[i], sn[i], P.a), sh), P.k);
         }
     }
 };

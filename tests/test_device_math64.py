@@ -2,7 +2,7 @@
 
 CPU part: the SAME header compiled for the host (tests/hostmath.cpp, MUFU seeds emulated at 20 bits)
 against libm / long-double references.  GPU part (-m gpu): the device build through
-mcb200_debug_math64.  Bars, written here: exp, sqrt, 1/x <= 2 ulp; cos/sin <= 3e-16 absolute;
+mcb200_debug_math64.  Bars, written here: exp (both argument conventions), sqrt, 1/x <= 2 ulp; cos/sin <= 3e-16 absolute;
 -2 ln u <= 2.5e-16 absolute + 3 ulp relative.
 """
 import ctypes as C
@@ -41,6 +41,10 @@ def check(run):
     edge = run(3, np.array([-700.0, 700.0, 0.0]))[:, 0]                          # the validated domain is |x| <= 700
     assert ulps(edge, np.exp(np.array([-700.0, 700.0, 0.0]))).max() <= 2
     assert np.isnan(run(3, np.array([np.nan]))[0, 0])
+    # the same exponential taking its argument in table units: 2^(y/256), |y| <= 700 * 256 / ln 2
+    y = np.concatenate([c["exp"] * 369.3299304675746, np.array([0.0, 0.5, -0.5, 1.5, 255.5, 256.0, -258000.0, 258000.0]),
+                        np.arange(-600.0, 600.0, 0.25)])
+    assert ulps(run(7, y)[:, 0], np.exp2(y.astype(np.longdouble) / 256).astype(np.float64)).max() <= 2
     assert ulps(run(1, c["sqrt"])[:, 0], np.sqrt(c["sqrt"])).max() <= 2
     assert ulps(run(6, c["sqrt"])[:, 0], np.sqrt(c["sqrt"])).max() <= 2      # short iteration (basket, CVA kernels)
     assert ulps(run(2, c["rcp"])[:, 0], 1.0 / c["rcp"]).max() <= 2
@@ -71,7 +75,7 @@ def hostmath(tmp_path_factory):
 
 
 def test_host_build_of_device_math(hostmath):
-    names = {0: "hm_neg2log", 1: "hm_sqrt", 2: "hm_rcp", 3: "hm_exp", 6: "hm_sqrt_short"}
+    names = {0: "hm_neg2log", 1: "hm_sqrt", 2: "hm_rcp", 3: "hm_exp", 6: "hm_sqrt_short", 7: "hm_exp_units"}
 
     def run(fn, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -32,10 +32,13 @@ struct SharedTables64Rep {
     Tables64Rep t;
     __device__ __forceinline__ void load()
     {
+        for (int i = threadIdx.x; i < kLogEntries * 8; i += blockDim.x) {
+            const int j = i >> 3, rep = i & 7;
+            t.log_rep[j][rep][0] = bias_log_recip(log_table_entry(j)[0]);
+            t.log_rep[j][rep][1] = log_table_entry(j)[1];
+        }
         for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
             const int j = i >> 3, rep = i & 7;
-            t.log_rep[j][rep][0] = bias_log_recip(kLogTable[j][0]);
-            t.log_rep[j][rep][1] = kLogTable[j][1];
             t.turn_lo_rep[j][rep][0] = kTurnLoTable[j][0];
             t.turn_lo_rep[j][rep][1] = kTurnLoTable[j][1];
         }

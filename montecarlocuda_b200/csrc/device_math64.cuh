@@ -102,16 +102,24 @@ MCB_FN uint32_t and_or(uint32_t a, uint32_t mask, uint32_t c)
 MCB_FN double bias_log_recip(double c) { return make_double(hi_word(c) + 0x3ff00000, lo_word(c)); }
 MCB_FN double bias_exp_entry(double t, int j) { return make_double(hi_word(t) - (j << 12), lo_word(t)); }
 
+// index bits of the logarithm's table: 8 -> 256 entries and a degree-6 log1p, 9 -> 512 entries and degree 5
+#ifndef MCB_LOG_BITS
+#define MCB_LOG_BITS 9
+#endif
+constexpr int kLogBits = MCB_LOG_BITS;
+constexpr int kLogEntries = 1 << kLogBits;
+MCB_FN const double *log_table_entry(int i) { return kLogBits == 9 ? kLogTable9[i] : kLogTable[i & 255]; }
+
 // Plain layout: host build, instrumentation and per-path kernels (their coarse angle table stays where the
 // generated one lies -- global memory on the device: 64 KB do not fit a static shared-memory allocation).
 struct Tables64 {
-    double log_tab[256][2];       // { c_i (biased), -ln c_i }
+    double log_tab[kLogEntries][2];       // { c_i (biased), -ln c_i }
     double exp_tab[256];          // 2^(j/256) (biased)
     double turn_lo[256][2];       // { cos, sin } of 2 pi j / 2^20
     // hi_u = high word of u: the entry of its top 8 mantissa bits
     MCB_MEMBER void log_entry(int hi_u, double &c, double &l) const
     {
-        const int i = (hi_u >> 12) & 0xff;
+        const int i = (hi_u >> (20 - kLogBits)) & (kLogEntries - 1);
         c = log_tab[i][0];
         l = log_tab[i][1];
     }
@@ -121,8 +129,10 @@ struct Tables64 {
     MCB_MEMBER void turn_lo_entry(uint32_t k, double &c, double &s) const { c = turn_lo[k & 255u][0]; s = turn_lo[k & 255u][1]; }
     MCB_MEMBER void fill(int i)   // for every i < 256
     {
-        log_tab[i][0] = bias_log_recip(kLogTable[i][0]);
-        log_tab[i][1] = kLogTable[i][1];
+        for (int j = i; j < kLogEntries; j += 256) {
+            log_tab[j][0] = bias_log_recip(log_table_entry(j)[0]);
+            log_tab[j][1] = log_table_entry(j)[1];
+        }
         exp_tab[i] = bias_exp_entry(kExpTable[i], i);
         turn_lo[i][0] = kTurnLoTable[i][0];
         turn_lo[i][1] = kTurnLoTable[i][1];
@@ -158,13 +168,13 @@ struct Tables64Wide : Tables64 {
 // (192 KB) had been measured slower (profiles/r01p_ab_experiments.txt) -- with pointer arithmetic, not the one-LOP3
 // offsets used here.  160 KB in all, one table set per SM shared by the CTA's sub-blocks.
 struct Tables64Rep {
-    double log_rep[256][8][2];       // [index][replica]{ c_i (biased), -ln c_i }        32 KB
+    double log_rep[kLogEntries][8][2];   // [index][replica]{ c_i (biased), -ln c_i }        32 KB
     double exp_rep[256][16];         // [index][replica] 2^(j/256) (biased)             32 KB
     double turn_lo_rep[256][8][2];   // [index][replica]{ cos, sin } of 2 pi j / 2^20   32 KB
     double turn_hi[4096][2];         // { cos, sin } of 2 pi i / 4096                   64 KB
     MCB_MEMBER void log_entry(int hi_u, double &c, double &l) const
     {
-        const uint32_t off = and_or((uint32_t)hi_u >> 5, 0x7f80u, (threadIdx.x & 7u) << 4);
+        const uint32_t off = and_or((uint32_t)hi_u >> (13 - kLogBits), (uint32_t)(kLogEntries - 1) << 7, (threadIdx.x & 7u) << 4);
         const double2 v = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(log_rep) + off);
         c = v.x;
         l = v.y;
@@ -234,8 +244,13 @@ template <class Tab> MCB_FN double scaled_log_unit(double u, const Tab &T, doubl
     double c, l;
     T.log_entry(hi, c, l);
     const double r = fma_(u, make_double(hi_word(c) - ebits, lo_word(c)), -1.0);
-    double q = fma_(r, -1.0 / 6.0, 0.2);
-    q = fma_(r, q, -0.25);
+    double q;
+    if (kLogBits == 9) {
+        q = fma_(r, 0.2, -0.25);                           // r < 2^-9: r^6/6 < 2^-56
+    } else {
+        q = fma_(r, -1.0 / 6.0, 0.2);
+        q = fma_(r, q, -0.25);
+    }
     q = fma_(r, q, 1.0 / 3.0);
     q = fma_(r, q, -0.5);
     const double p = fma_(r * r, q, r);                    // log1p(r)

@@ -226,7 +226,10 @@ struct Basket {
     };
     static constexpr bool kSharedFactor = Table::kSharedFactor;
     // fp64 pricing kernels from 8 assets up read the factor from shared memory too (see SharedFactor64)
-    static constexpr bool kSharedFactor64 = kAccumLayout && sizeof(RealT) == 8 && N >= 8 && N <= 16;  // wider: ptxas spills more than it saves
+#ifndef MCB_BASKET_SHARED_FACTOR64
+#define MCB_BASKET_SHARED_FACTOR64 1
+#endif
+    static constexpr bool kSharedFactor64 = MCB_BASKET_SHARED_FACTOR64 && kAccumLayout && sizeof(RealT) == 8 && N >= 8 && N <= 16;  // wider: ptxas spills more than it saves
     using Shared = std::conditional_t<
         kTwoPass, SharedTwoPass64<kHalf>,
         std::conditional_t<

@@ -43,21 +43,22 @@ struct alignas(16) CvaDate {  // three 16-byte constant loads per date
 __constant__ __align__(16) unsigned char c_cva_table[kCvaMaxDates * sizeof(CvaDate<double>)];
 static TableLock g_cva_lock;
 
-// q(d) = cnd-tail(|d|) / (sqrt(2 pi) phi(d)) = k polynomial(k), k = 1 / (1 + 0.2316419 |d|)
-// (Abramowitz-Stegun 26.2.17, the constants of DP/MonteCarloKernel.cu:111-116 times 1/sqrt(2 pi))
+// q(d) = cnd-tail(|d|) / (sqrt(2 pi) phi(d)) = k P(k), k = 1 / (1 + 0.2316419 |d|)
+// (Abramowitz-Stegun 26.2.17, the constants of DP/MonteCarloKernel.cu:111-116 times 1/sqrt(2 pi)).  Returned as the
+// two factors: the caller needs sgn(d1) q1 - sgn(d2) q2, which is one multiply and one FMA on (k, P) pairs with the
+// signs put on the k's -- a multiply, a multiply and a subtraction on finished q's.
 template <typename Real>
-__device__ __forceinline__ Real hastings_ratio(Real d)
+__device__ __forceinline__ void hastings_factors(Real d, Real &k, Real &poly)
 {
     constexpr double c = 0.39894228040143267793994605993438;
-    const Real k = rcp_real(fma((Real)0.2316419, fabs(d), (Real)1.0));
-    Real poly = fma(k, (Real)(1.330274429 * c), (Real)(-1.821255978 * c));
+    k = rcp_real(fma((Real)0.2316419, fabs(d), (Real)1.0));
+    poly = fma(k, (Real)(1.330274429 * c), (Real)(-1.821255978 * c));
     poly = fma(k, poly, (Real)(1.781477937 * c));
     poly = fma(k, poly, (Real)(-0.356563782 * c));
     poly = fma(k, poly, (Real)(0.31938153 * c));
-    return k * poly;
 }
 
-// sgn(d) q for q > 0 and x [d > 0], by the sign bit of d on the integer pipe (the fp64 comparisons are
+// sgn(d) k for k > 0 and x [d > 0], by the sign bit of d on the integer pipe (the fp64 comparisons are
 // DSETPs on the pipe that binds).  d = +0 counts as positive where the reference's `d > 0` does not:
 // cnd(0) is 1/2 from either branch.
 __device__ __forceinline__ double with_sign_of(double q, double d)
@@ -122,7 +123,10 @@ struct Cva {
         // before maturity) or -inf (exact grid, tau = 0): floor it where e^x is already 0 for every purpose, so the
         // table-driven exp stays in range
         const Real a = exp_scaled(floor_exponent(fma(P.half_unit * d1, d1, y)), sh);
-        const Real tails = with_sign_of(hastings_ratio<Real>(d1), d1) - with_sign_of(hastings_ratio<Real>(d2), d2);
+        Real k1, p1, k2, p2;
+        hastings_factors(d1, k1, p1);
+        hastings_factors(d2, k2, p2);
+        const Real tails = fma(with_sign_of(k1, d1), p1, -(with_sign_of(k2, d2) * p2));
         const Real ee = fma(-a, tails, keep_if_positive(s, d1) - keep_if_positive(D.kd, d2));
         cva = fma(D.w, ee, cva);
     }

@@ -37,13 +37,11 @@ struct SharedTables64Rep {
             t.log_rep[j][rep][0] = bias_log_recip(log_table_entry(j)[0]);
             t.log_rep[j][rep][1] = log_table_entry(j)[1];
         }
-        for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-            const int j = i >> 3, rep = i & 7;
-            t.turn_lo_rep[j][rep][0] = kTurnLoTable[j][0];
-            t.turn_lo_rep[j][rep][1] = kTurnLoTable[j][1];
+        for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+            const int j = i >> 4, rep = i & 15;
+            t.rows[j].exp[rep] = bias_exp_entry(kExpTable[j], j);
+            t.rows[j].turn_lo[rep >> 1][rep & 1] = kTurnLoTable[j][rep & 1];
         }
-        for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x)
-            t.exp_rep[i >> 4][i & 15] = bias_exp_entry(kExpTable[i >> 4], i >> 4);
         for (int i = threadIdx.x; i < 4096; i += blockDim.x)
             *reinterpret_cast<double2 *>(t.turn_hi[i]) = *reinterpret_cast<const double2 *>(kTurnHiTable[i]);
     }

@@ -168,10 +168,14 @@ struct Tables64Wide : Tables64 {
 // (192 KB) had been measured slower (profiles/r01p_ab_experiments.txt) -- with pointer arithmetic, not the one-LOP3
 // offsets used here.  160 KB in all, one table set per SM shared by the CTA's sub-blocks.
 struct Tables64Rep {
-    double log_rep[kLogEntries][8][2];   // [index][replica]{ c_i (biased), -ln c_i }        32 KB
-    double exp_rep[256][16];         // [index][replica] 2^(j/256) (biased)             32 KB
-    double turn_lo_rep[256][8][2];   // [index][replica]{ cos, sin } of 2 pi j / 2^20   32 KB
-    double turn_hi[4096][2];         // { cos, sin } of 2 pi i / 4096                   64 KB
+    double log_rep[kLogEntries][8][2];   // [index][replica]{ c_i (biased), -ln c_i }                      64 KB
+    // the two 256-entry tables share rows of 256 bytes: a row's byte offset is then the index byte moved up by one
+    // byte, and "index byte of a word, plus this thread's replica" is ONE byte permute (PRMT)
+    struct Row {
+        double exp[16];          // [replica] 2^(j/256) (biased)
+        double turn_lo[8][2];    // [replica]{ cos, sin } of 2 pi j / 2^20
+    } rows[256];                 //                                                                        64 KB
+    double turn_hi[4096][2];     // { cos, sin } of 2 pi i / 4096                                          64 KB
     MCB_MEMBER void log_entry(int hi_u, double &c, double &l) const
     {
         const uint32_t off = and_or((uint32_t)hi_u >> (13 - kLogBits), (uint32_t)(kLogEntries - 1) << 7, (threadIdx.x & 7u) << 4);
@@ -179,10 +183,11 @@ struct Tables64Rep {
         c = v.x;
         l = v.y;
     }
+    // { 0, 0, low byte of index, offset inside the row }
+    static MCB_MEMBER uint32_t row_offset(uint32_t index, uint32_t inside) { return __byte_perm(index, inside, 0x6504); }
     MCB_MEMBER double exp_entry(int n) const
     {
-        const uint32_t off = and_or((uint32_t)n << 7, 0x7f80u, (threadIdx.x & 15u) << 3);
-        return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(exp_rep) + off);
+        return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(rows) + row_offset((uint32_t)n, (threadIdx.x & 15u) << 3));
     }
     MCB_MEMBER void turn_hi_entry(uint32_t k, double &c, double &s) const
     {
@@ -192,8 +197,8 @@ struct Tables64Rep {
     }
     MCB_MEMBER void turn_lo_entry(uint32_t k, double &c, double &s) const
     {
-        const uint32_t off = and_or(k << 7, 0x7f80u, (threadIdx.x & 7u) << 4);
-        const double2 v = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(turn_lo_rep) + off);
+        const double2 v = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(rows) +
+                                                             row_offset(k, 128u + ((threadIdx.x & 7u) << 4)));
         c = v.x;
         s = v.y;
     }

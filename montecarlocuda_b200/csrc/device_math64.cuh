@@ -165,8 +165,8 @@ struct Tables64Wide : Tables64 {
 // coarse one (4096 entries, 64 KB) stays a single copy at 2.6 wavefronts per quarter-warp.  With the 10 + 10 split of
 // round 1 (two single 16 KB tables) the angle look-ups were 22 of the 29 wavefronts of a Box-Muller pair and the
 // shared-memory pipe the busiest unit of the fp64 call (68 %) and the 10-asset basket (79 %); four copies of each
-// (192 KB) had been measured slower (profiles/r01p_ab_experiments.txt) -- with pointer arithmetic, not the one-LOP3
-// offsets used here.  160 KB in all, one table set per SM shared by the CTA's sub-blocks.
+// (192 KB) had been measured slower (profiles/r01p_ab_experiments.txt) -- with pointer arithmetic, not the one-
+// instruction offsets used here.  192 KB in all, one table set per SM shared by the CTA's sub-blocks.
 struct Tables64Rep {
     double log_rep[kLogEntries][8][2];   // [index][replica]{ c_i (biased), -ln c_i }                      64 KB
     // the two 256-entry tables share rows of 256 bytes: a row's byte offset is then the index byte moved up by one

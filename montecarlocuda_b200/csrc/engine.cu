@@ -175,9 +175,12 @@ PhiloxKeys make_keys(uint64_t seed)
 // at >= 2^16 chunks for large jobs and at most 64 units per thread
 int chunk_rounds(uint64_t total_units)
 {
-    const uint64_t q = total_units >> 24;
+#ifndef MCB_EXP_ROUNDS_SHIFT
+#define MCB_EXP_ROUNDS_SHIFT 0   // experiment only (tools/build_variant.sh): longer chunks, to size the cost of a commit
+#endif
+    const uint64_t q = total_units >> (24 - MCB_EXP_ROUNDS_SHIFT);
     int r = 1;
-    while (r < 64 && (uint64_t)(r * 2) <= q)
+    while (r < (64 << MCB_EXP_ROUNDS_SHIFT) && (uint64_t)(r * 2) <= q)
         r *= 2;
     return r;
 }

@@ -254,10 +254,14 @@ __device__ __forceinline__ void basket_tc_store16(const float *z, uint32_t lane_
 {
     uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const uint32_t h = __float_as_uint(z[i]) & 0xffffe000u;
-        hi[i] = h;
-        lo[i] = __float_as_uint(z[i] - __uint_as_float(h));
+    for (int i = 0; i < 16; i += 2) {
+        hi[i] = __float_as_uint(z[i]) & 0xffffe000u;
+        hi[i + 1] = __float_as_uint(z[i + 1]) & 0xffffe000u;
+        // lo = z - hi (exact), two columns per packed instruction
+        float l0, l1;
+        sub_f32x2(z[i], z[i + 1], __uint_as_float(hi[i]), __uint_as_float(hi[i + 1]), l0, l1);
+        lo[i] = __float_as_uint(l0);
+        lo[i + 1] = __float_as_uint(l1);
     }
     tc::st16(lane_d + 64 + col, hi);
     tc::st16(lane_d + 96 + col, lo);

@@ -101,6 +101,72 @@ __device__ __forceinline__ float mufu_cos(float x)
     return y;
 }
 
+// Packed fp32 arithmetic (sm_100: add / mul / fma .f32x2 -- FADD2, FMUL2, FFMA2): two independent IEEE operations in one
+// issue slot.  The fp32 kernels are bound by issue slots around their MUFU chain, so wherever two
+// scalar operations of the same kind sit side by side with no shared operand to duplicate, they go out as one.
+// Results are bit-identical to the scalar instructions.
+#ifndef MCB_PACKED_F32
+#define MCB_PACKED_F32 1
+#endif
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi)
+{
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// (d0, d1) = (a0, a1) * (b, b) + (c, c)
+__device__ __forceinline__ void fma_f32x2(float a0, float a1, float b, float c, float &d0, float &d1)
+{
+#if MCB_PACKED_F32
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b, b)), "l"(pack_f32x2(c, c)));
+    unpack_f32x2(d, d0, d1);
+#else
+    d0 = fmaf(a0, b, c);
+    d1 = fmaf(a1, b, c);
+#endif
+}
+// (d0, d1) = (a0, a1) * (b, b)
+__device__ __forceinline__ void mul_f32x2(float a0, float a1, float b, float &d0, float &d1)
+{
+#if MCB_PACKED_F32
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b, b)));
+    unpack_f32x2(d, d0, d1);
+#else
+    d0 = a0 * b;
+    d1 = a1 * b;
+#endif
+}
+// (d0, d1) = (a0, a1) - (b0, b1)
+__device__ __forceinline__ void sub_f32x2(float a0, float a1, float b0, float b1, float &d0, float &d1)
+{
+#if MCB_PACKED_F32
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)));
+    unpack_f32x2(d, d0, d1);
+#else
+    d0 = a0 - b0;
+    d1 = a1 - b1;
+#endif
+}
+// (d0, d1) = (a0, a1) + (c, c)
+__device__ __forceinline__ void add_f32x2(float a0, float a1, float c, float &d0, float &d1)
+{
+#if MCB_PACKED_F32
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(c, c)));
+    unpack_f32x2(d, d0, d1);
+#else
+    d0 = a0 + c;
+    d1 = a1 + c;
+#endif
+}
+
 // fp32: one Philox block (128 bits) serves THREE Box-Muller pairs, i.e. six normals.  Pair i takes 42
 // consecutive bits of the block read as one 128-bit string w0:w1:w2:w3 (w0 most significant): 23 for the
 // radius uniform, then 19 for the angle; the last 2 bits are unused.
@@ -129,25 +195,39 @@ __device__ __forceinline__ void uniforms_f32(const uint32_t (&w)[4], float (&f)[
     f[5] = stuff_f32(w[3] << 2, kAngle);                              // bits 107..125: w3[20:2]
 }
 
-// One Box-Muller pair from its two stuffed uniforms.  radius: u = 2 - f in (0, 1], r = sqrt(-2 ln u);
-// angle: 2*pi*(f - 1.5) in [-pi, pi) as one FFMA, the range where MUFU.SIN/COS are most accurate.
-// 4 MUFU per pair (LG2, SQRT, SIN, COS).
-__device__ __forceinline__ void box_muller_f32(float fr, float fa, float &z0, float &z1)
+// One Box-Muller pair from its two stuffed uniforms: radius u = 2 - f in (0, 1], r = sqrt(-2 ln u) = sqrt(-2 ln2 lg2 u);
+// angle 2 pi (f - 1.5) in [-pi, pi) as one FFMA, the range where MUFU.SIN/COS are most accurate.  4 MUFU per pair (LG2,
+// SQRT, SIN, COS).
+// (r, cos, sin) of a block's three pairs: r = sqrt(c lg2(u)) -- c = -2 ln 2 for a standard normal pair, times b^2 for
+// a caller that wants b r (polar_from_words below).  Pairs 0 and 1 go side by side on packed instructions.
+__device__ __forceinline__ void polar_f32(const uint32_t (&w)[4], float c, float (&r)[3], float (&cs)[3], float (&sn)[3])
 {
-    const float u = 2.0f - fr;
-    const float r = mufu_sqrt(mufu_lg2(u) * -1.3862943611198906f);  // -2 ln2 * log2(u)
-    const float a = fmaf(fa, 6.283185307179586f, -9.42477796076938f);
-    z0 = r * mufu_cos(a);
-    z1 = r * mufu_sin(a);
+    float f[6];
+    uniforms_f32(w, f);
+    float u[3], ang[3], l[3];
+    fma_f32x2(f[0], f[2], -1.0f, 2.0f, u[0], u[1]);                    // 2 - f exactly, as the scalar subtraction
+    u[2] = 2.0f - f[4];
+    fma_f32x2(f[1], f[3], 6.283185307179586f, -9.42477796076938f, ang[0], ang[1]);
+    ang[2] = fmaf(f[5], 6.283185307179586f, -9.42477796076938f);
+    mul_f32x2(mufu_lg2(u[0]), mufu_lg2(u[1]), c, l[0], l[1]);
+    l[2] = mufu_lg2(u[2]) * c;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        r[i] = mufu_sqrt(l[i]);
+        cs[i] = mufu_cos(ang[i]);
+        sn[i] = mufu_sin(ang[i]);
+    }
 }
 
 __device__ __forceinline__ void normals_from_words(const uint32_t (&w)[4], float (&z)[6], const NoShared &)
 {
-    float f[6];
-    uniforms_f32(w, f);
-    box_muller_f32(f[0], f[1], z[0], z[1]);
-    box_muller_f32(f[2], f[3], z[2], z[3]);
-    box_muller_f32(f[4], f[5], z[4], z[5]);
+    float r[3], cs[3], sn[3];
+    polar_f32(w, -1.3862943611198906f, r, cs, sn);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        z[2 * i] = r[i] * cs[i];
+        z[2 * i + 1] = r[i] * sn[i];
+    }
 }
 
 // ---- fp64 ----
@@ -222,15 +302,7 @@ template <bool kShortSqrt = true>
 __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], float (&br)[3], float (&cs)[3], float (&sn)[3],
                                                  const NoShared &, const PolarScale<float> &S, const NoJobState &)
 {
-    float f[6];
-    uniforms_f32(w, f);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        br[i] = mufu_sqrt(mufu_lg2(2.0f - f[2 * i]) * S.c);
-        const float ang = fmaf(f[2 * i + 1], 6.283185307179586f, -9.42477796076938f);
-        cs[i] = mufu_cos(ang);
-        sn[i] = mufu_sin(ang);
-    }
+    polar_f32(w, S.c, br, cs, sn);
 }
 template <bool kShortSqrt = true, class Sh>
 __device__ __forceinline__ void polar_from_words(const uint32_t (&w)[4], double (&br)[2], double (&cs)[2], double (&sn)[2],

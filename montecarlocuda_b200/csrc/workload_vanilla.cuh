@@ -50,13 +50,6 @@ struct Vanilla {
     // fp64: eval returns S_T - K and add_value clamps (sign test + predicated accumulation); fp32: one FMNMX here
     static constexpr bool kClampAtZero = sizeof(Real) == 8;
     static __device__ __forceinline__ void prepare(const Params &P, JobState &job, int tid) { prepare_polar(P.scale, job, tid); }
-    static __device__ __forceinline__ Real payoff(Real s_t, Real k)
-    {
-        if constexpr (kClampAtZero)
-            return s_t - k;
-        else
-            return positive_part(s_t - k);
-    }
     static __device__ __forceinline__ void eval(const Params &P, uint32_t unit_lo, uint32_t unit_hi,
                                                 Real (&v)[kUnitPaths], const Shared &sh, const JobState &job)
     {
@@ -69,8 +62,15 @@ struct Vanilla {
         polar_from_words<MCB_VANILLA_SHORT_SQRT>(w, br, cs, sn, sh, P.scale, job);
 #pragma unroll
         for (int i = 0; i < kPairs; i++) {
-            v[2 * i] = payoff(exp_scaled(fma(br[i], cs[i], P.a), sh), P.k);
-            v[2 * i + 1] = payoff(exp_scaled(fma(br[i], sn[i], P.a), sh), P.k);
+            const Real s0 = exp_scaled(fma(br[i], cs[i], P.a), sh), s1 = exp_scaled(fma(br[i], sn[i], P.a), sh);
+            if constexpr (sizeof(Real) == 4) {
+                add_f32x2(s0, s1, -P.k, v[2 * i], v[2 * i + 1]);     // one FADD2 for the pair's two S_T - K
+                v[2 * i] = positive_part(v[2 * i]);
+                v[2 * i + 1] = positive_part(v[2 * i + 1]);
+            } else {
+                v[2 * i] = s0 - P.k;          // add_value clamps
+                v[2 * i + 1] = s1 - P.k;
+            }
         }
     }
 };

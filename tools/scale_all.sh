@@ -13,7 +13,7 @@ run() { # n tag extra...
   tail -c 300 gpurun_out/scale_$tag.err | tail -2
 }
 run 8 8
-run 8 8_wait --peer-mode wait
+if [ -z "$NOWAIT" ]; then run 8 8_wait --peer-mode wait; fi
 if [ -z "$QUICK" ]; then
 run 4 4
 run 2 2

@@ -84,6 +84,39 @@ def test_chunk_reduction_bit_exact(engine, oracle, in_float, unit_paths, rounds,
     assert np.array_equal(acc, want)
 
 
+@pytest.mark.parametrize("value,scale_sum,scale_sumsq", [
+    (17.25, 73, 66),                  # the common case: three limbs in the middle of the window
+    (3.0, 0, 0), (0.75, 0, 1),        # p < 0: bits below the window's lsb are truncated (sum: floor(3), sumsq: 9 / floor(1.125))
+    (2.0 ** -40, 20, 20),             # entirely below the lsb: zero limbs, no error
+    (1.0, 158, 105), (1.5, 157, 52),  # top limb: the last values that fit (2^158 resp. the square's 2.25 * 2^52)
+    (1.0, 159, 0),                    # 2^159 does not fit the 160-bit window with its headroom bit: error flag
+    (2.0 ** 60, 64, -70),             # limb boundaries: off = 12 -> the spill into the third limb starts
+    (5e-324, 1074, 0), (2.0 ** -1060, 1100, 1000),   # denormals (the high-word clamp leaves such values behind)
+    (1e300, -900, -1900), (1e-300, 1000, 2000),      # far ends of the exponent range
+])
+def test_limb_split_edge_cases(engine, oracle, value, scale_sum, scale_sumsq):
+    """lanes_add runs in integer arithmetic on the device (device_common.cuh) and in floating point in the oracle
+    (ldexp, three conversions): the two must agree bit for bit everywhere, including truncation below the window,
+    its top limb, denormals, and on WHEN a value is refused."""
+    vals = np.array([value])
+    acc = engine.reduce_chunk(vals, 1, 1, False, scale_sum, scale_sumsq)
+    want = np.zeros(12, dtype=np.uint64)
+    bad = oracle.lanes_add(value, scale_sum, want[0:5]) + oracle.lanes_add(value * value, scale_sumsq, want[5:10])
+    want[10], want[11] = 1, bad
+    assert np.array_equal(acc, want), (acc, want)
+
+
+@pytest.mark.parametrize("value", [-1.0, float("nan"), float("inf"), -0.0])
+def test_limb_split_refuses_what_the_oracle_refuses(engine, oracle, value):
+    acc = engine.reduce_chunk(np.array([value]), 1, 1, False, 73, 66)
+    want = np.zeros(12, dtype=np.uint64)
+    sq = value * value
+    bad = oracle.lanes_add(value, 73, want[0:5]) + oracle.lanes_add(sq, 66, want[5:10])
+    want[10], want[11] = 1, bad
+    assert np.array_equal(acc, want), (acc, want)
+    assert (bad > 0) == (not (value >= 0.0) or np.isinf(value))
+
+
 # ------------------------------------------------------------------------------------------------
 # per-path values vs the oracle on the same stream
 # ------------------------------------------------------------------------------------------------

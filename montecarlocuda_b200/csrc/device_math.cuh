@@ -320,9 +320,8 @@ template <typename Real> struct NormalsPerBlock;
 template <> struct NormalsPerBlock<float> { static constexpr int value = 6; };
 template <> struct NormalsPerBlock<double> { static constexpr int value = 4; };
 
-// max(x, 0): FMNMX for fp32; for fp64 an integer mask (fmax(double) is DSETP + selects + NaN fix-up)
+// max(x, 0) for fp32: one FMNMX (the fp64 kernels leave the clamp to add_value, device_common.cuh)
 __device__ __forceinline__ float positive_part(float x) { return fmaxf(x, 0.0f); }
-__device__ __forceinline__ double positive_part(double x) { return relu64(x); }
 
 // precision-generic wrappers used by the workload policies.  exp_scaled takes its argument in the units the
 // exponential is cheapest in -- log2 units for fp32 (MUFU.EX2), units of ln2/256 for fp64 (exp_units) -- and
@@ -332,8 +331,6 @@ template <> struct ExpUnit<float> { static constexpr double value = 1.4426950408
 template <> struct ExpUnit<double> { static constexpr double value = 369.32993046757463228; };           // 256 / ln 2
 template <class Sh> __device__ __forceinline__ float exp_scaled(float x, const Sh &) { return mufu_ex2(x); }
 template <class Sh> __device__ __forceinline__ double exp_scaled(double y, const Sh &sh) { return exp_units(y, sh.t); }
-__device__ __forceinline__ float exp_real(float x, const NoShared &) { return mufu_ex2(x * 1.4426950408889634f); }
-template <class Sh> __device__ __forceinline__ double exp_real(double x, const Sh &sh) { return exp_tab(x, sh.t); }
 __device__ __forceinline__ float rcp_real(float x) { return mufu_rcp(x); }
 __device__ __forceinline__ double rcp_real(double x) { return rcp_newton(x); }
 

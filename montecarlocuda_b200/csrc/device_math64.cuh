@@ -383,14 +383,6 @@ template <class Tab> MCB_FN double exp_tab(double x, const Tab &T)
     return fma_(ts, p, ts);
 }
 
-// ---- max(x, 0) on the integer pipe: clear every bit when the sign bit is set ----------------------
-MCB_FN double relu64(double x)
-{
-    const int hi = hi_word(x);
-    const int keep = ~(hi >> 31);
-    return make_double(hi & keep, lo_word(x) & keep);
-}
-
 #ifdef MCB_HOST_MATH
 }  // namespace hostmath
 #endif

@@ -43,7 +43,7 @@ enum { MCB200_F32 = 0, MCB200_F64 = 1 };
 enum { MCB200_VANILLA = 1, MCB200_BASKET = 2, MCB200_CVA = 3 };
 
 #define MCB200_MAX_ASSETS 64
-#define MCB200_MAX_DATES 1024
+#define MCB200_MAX_DATES (1 << 20) /* exposure dates of a CVA grid (up to 1024 kept dates sit in constant memory, longer grids in device memory) */
 #define MCB200_LANES 5
 /* accumulator block: [0..4] sum limbs, [5..9] sum-of-squares limbs, [10] paths counted,
  * [11] error flags.  Each limb carries a 32-bit payload in a 64-bit word, so blocks from

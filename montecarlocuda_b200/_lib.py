@@ -16,7 +16,7 @@ VANILLA, BASKET, CVA = 1, 2, 3
 ACC_WORDS = 12
 LANES = 5
 MAX_ASSETS = 64
-MAX_DATES = 1024
+MAX_DATES = 1 << 20
 
 
 class Mcb200Error(RuntimeError):

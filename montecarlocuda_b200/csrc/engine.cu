@@ -416,7 +416,7 @@ int blocks_per_sm(const mcb200_plan_t &plan, const AnyJob &job)
     switch (plan.workload) {
         case MCB200_VANILLA: return vanilla_blocks_per_sm(plan.precision);
         case MCB200_BASKET: return basket_blocks_per_sm(plan.precision, job.basket.job.n, job.basket.job.full);
-        default: return cva_blocks_per_sm(plan.precision);
+        default: return cva_blocks_per_sm(plan.precision, job.cva.job.n_dates);
     }
 }
 
@@ -1247,7 +1247,8 @@ int mcb200_price_batch(mcb200_ctx *ctx, int n_jobs, const mcb200_job_t *jobs, mc
         for (int precision : {MCB200_F32, MCB200_F64}) {
             std::vector<int> members;
             for (int i = 0; i < n_jobs; i++)
-                if (status[i] == MCB200_OK && jobs[i].workload == workload && jobs[i].precision == precision)
+                if (status[i] == MCB200_OK && jobs[i].workload == workload && jobs[i].precision == precision &&
+                    !(workload == MCB200_CVA && built[i].cva.job.n_dates > kCvaMaxDates))   // a long grid has its own table and launch
                     members.push_back(i);
             if (members.size() < 2)
                 continue;  // a lone job takes the one-job kernel below (its parameters sit in the constant bank)

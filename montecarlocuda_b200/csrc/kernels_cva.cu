@@ -91,7 +91,9 @@ __device__ __forceinline__ double floor_exponent(double a)
 }
 __device__ __forceinline__ float floor_exponent(float a) { return a; }  // MUFU.EX2(-inf) = 0
 
-template <typename RealT, bool kAccumLayout = false>
+// kGlobalDates: the date table does not fit the constant buffer (more than kCvaMaxDates kept dates) and is read from
+// device memory through Params::dates_global instead -- the same uniform loads, through L1 instead of the constant cache
+template <typename RealT, bool kAccumLayout = false, bool kGlobalDates = false>
 struct Cva {
     using Real = RealT;
     static constexpr int kUnitPaths = 1;
@@ -106,6 +108,7 @@ struct Cva {
         PolarScale<Real> scale;  // of sig_dt = v sqrt(dt) (same units), folded under the Box-Muller square root
         int n_dates;  // kept dates
         int first_date;  // of this job in the device table (0 unless the launch carries several jobs)
+        const void *dates_global;  // kGlobalDates: CvaDate<Real>[n_dates] in device memory
     };
     using Shared = std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>;
     using JobState = typename JobStateFor<Real>::type;
@@ -133,7 +136,8 @@ struct Cva {
     static __device__ __forceinline__ void eval(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1],
                                                 const Shared &sh, const JobState &job)
     {
-        const CvaDate<Real> *dates = reinterpret_cast<const CvaDate<Real> *>(c_cva_table) + P.first_date;
+        const CvaDate<Real> *dates = kGlobalDates ? static_cast<const CvaDate<Real> *>(P.dates_global)
+                                                  : reinterpret_cast<const CvaDate<Real> *>(c_cva_table) + P.first_date;
         Real y = P.y0, cva = 0;
         // whole draw blocks run their kNpb dates back to back with no test in between: only y links one date to the
         // next, so the exponentials and reciprocals of neighbouring dates overlap
@@ -184,6 +188,7 @@ static typename W::Params narrow(const CvaJob &job)
     p.scale = polar_scale<Real>(job.sig_dt * unit);
     p.n_dates = job.n_dates;
     p.first_date = 0;
+    p.dates_global = nullptr;
     return p;
 }
 
@@ -205,9 +210,9 @@ static cudaError_t upload_dates(TableUse &use, const std::vector<CvaDate<Real>> 
     return cudaSuccess;
 }
 template <typename Real>
-static bool stage_dates(const CvaJob &job, std::vector<CvaDate<Real>> &staging)
+static bool stage_dates(const CvaJob &job, std::vector<CvaDate<Real>> &staging, size_t capacity = (size_t)kCvaMaxDates)
 {
-    if (job.n_dates < 0 || staging.size() + (size_t)job.n_dates > (size_t)kCvaMaxDates)
+    if (job.n_dates < 0 || staging.size() + (size_t)job.n_dates > capacity)
         return false;
     for (int j = 0; j < job.n_dates; j++) {
         const CvaDateHost &h = job.dates[j];
@@ -218,11 +223,75 @@ static bool stage_dates(const CvaJob &job, std::vector<CvaDate<Real>> &staging)
     return true;
 }
 
+// ---- long grids: more kept dates than the constant buffer holds ----
+// One growable device buffer per device, shared like the constant table (same lock discipline, same "skip the upload
+// when the device already holds this image").  The reference has no limit here (cva->n is a plain int,
+// DP/MonteCarloKernel.cu:247); neither has this path, up to MCB200_MAX_DATES.
+static TableLock g_cva_wide_lock;
+static void *g_cva_wide_buffer[TableLock::kMaxDevices] = {};
+static size_t g_cva_wide_capacity[TableLock::kMaxDevices] = {};
+
+template <typename Real>
+static cudaError_t launch_wide_t(const CvaJob &job, const Geometry *geom, int grid, unsigned long long *d_acc,
+                                 unsigned long long first_unit, unsigned long long n_units, void *d_out,
+                                 cudaStream_t stream, const LaunchOptions &opt)
+{
+    std::vector<CvaDate<Real>> staging;
+    if (!stage_dates(job, staging, (size_t)job.n_dates))
+        return cudaErrorInvalidValue;
+    const size_t bytes = staging.size() * sizeof(CvaDate<Real>);
+    TableUse use(g_cva_wide_lock, stream, staging.data(), bytes);
+    if (use.status() != cudaSuccess)
+        return use.status();
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess)
+        return e;
+    if (g_cva_wide_capacity[device] < bytes) {
+        // (cudaFree waits for everything that may still read the old buffer)
+        use.invalidate();
+        if (g_cva_wide_buffer[device])
+            cudaFree(g_cva_wide_buffer[device]);
+        g_cva_wide_buffer[device] = nullptr;
+        g_cva_wide_capacity[device] = 0;
+        e = cudaMalloc(&g_cva_wide_buffer[device], bytes);
+        if (e != cudaSuccess)
+            return e;
+        g_cva_wide_capacity[device] = bytes;
+    }
+    if (use.needs_upload() || g_cva_wide_buffer[device] == nullptr) {
+        e = cudaMemcpyAsync(g_cva_wide_buffer[device], staging.data(), bytes, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) {
+            use.invalidate();
+            return e;
+        }
+        use.uploaded();
+    }
+    if (geom) {
+        using W = Cva<Real, true, true>;
+        typename W::Params p = narrow<W>(job);
+        p.dates_global = g_cva_wide_buffer[device];
+        e = accumulate_launch<W>(grid, p, *geom, d_acc, stream, opt);
+    } else {
+        using W = Cva<Real, false, true>;
+        typename W::Params p = narrow<W>(job);
+        p.dates_global = g_cva_wide_buffer[device];
+        const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
+        mc_paths_kernel<W><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(p, first_unit, n_units, (Real *)d_out);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess)
+        use.invalidate();
+    return e;
+}
+
 template <typename Real>
 static cudaError_t launch_t(const CvaJob &job, const Geometry *geom, int grid, unsigned long long *d_acc,
                             unsigned long long first_unit, unsigned long long n_units, void *d_out,
                             cudaStream_t stream, const LaunchOptions &opt)
 {
+    if (job.n_dates > kCvaMaxDates)
+        return launch_wide_t<Real>(job, geom, grid, d_acc, first_unit, n_units, d_out, stream, opt);
     std::vector<CvaDate<Real>> staging;
     if (!stage_dates(job, staging))
         return cudaErrorInvalidValue;
@@ -285,8 +354,10 @@ cudaError_t cva_batch_launch(int precision, const BatchShape &shape, const CvaJo
     return precision ? batch_t<double>(shape, jobs, grid, target, stream, opt) : batch_t<float>(shape, jobs, grid, target, stream, opt);
 }
 
-int cva_blocks_per_sm(int precision)
+int cva_blocks_per_sm(int precision, int n_dates)
 {
+    if (n_dates > kCvaMaxDates)
+        return precision ? accumulate_blocks_per_sm<Cva<double, true, true>>() : accumulate_blocks_per_sm<Cva<float, true, true>>();
     return precision ? accumulate_blocks_per_sm<Cva<double, true>>() : accumulate_blocks_per_sm<Cva<float, true>>();
 }
 

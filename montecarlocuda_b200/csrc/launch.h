@@ -79,7 +79,7 @@ cudaError_t basket_paths(int precision, const BasketJob &job, unsigned long long
                          unsigned long long n_units, void *d_out, cudaStream_t stream);
 
 // ---- CVA (DP/MonteCarloKernel.cu:104-129, :222-283) ----
-constexpr int kCvaMaxDates = 1024;
+constexpr int kCvaMaxDates = 1024;   // kept dates the constant table holds; longer grids are read from device memory
 struct CvaDateHost {
     double w, inv, c1, sig, kd;
 };
@@ -89,7 +89,7 @@ struct CvaJob {
     int n_dates;               // kept dates
     const CvaDateHost *dates;  // n_dates entries
 };
-int cva_blocks_per_sm(int precision);
+int cva_blocks_per_sm(int precision, int n_dates);
 cudaError_t cva_launch(int precision, const CvaJob &job, const Geometry &geom, int grid,
                        unsigned long long *d_acc, cudaStream_t stream, const LaunchOptions &opt);
 // jobs[i].dates are concatenated into the device table (kCvaMaxDates entries in all)

@@ -167,6 +167,32 @@ def test_cva_paths_match_oracle(engine, oracle, prec, n_dates):
     assert np.max(np.abs(got - want)) < tol
 
 
+@pytest.mark.parametrize("prec,n_dates", [("f64", 1025), ("f64", 1500), ("f32", 1100), ("f64", 4098)])
+def test_cva_long_grid_reads_its_dates_from_device_memory(engine, oracle, prec, n_dates):
+    """More kept dates than the 1024 of the constant table (the reference has no limit: cva->n is a plain int,
+    DP/MonteCarloKernel.cu:247): same kernel, date table in device memory.  Per-path values against the oracle,
+    the accumulator against the oracle's restatement applied to them bit for bit, the price against the closed form."""
+    cva = m.CVA(0.03, 0.6, m.OptionData(100.0, 100.0, 0.05, 0.2, 1.0), n_dates)
+    n, seed = 1024, 99
+    got = engine.cva_paths(cva, 0, n, prec, seed)
+    want = oracle.cva_path_values(100.0, 100.0, 0.05, 0.2, 1.0, 0.03, 0.6, n_dates, seed, 0, n, prec).astype(np.float64)
+    tol = 2e-11 if prec == "f64" else 2e-3      # the error budget of test_cva_paths_match_oracle, for 20-80 times the dates
+    assert np.max(np.abs(got.astype(np.float64) - want)) < tol
+    p = m.plan("cva", cva, n, prec)
+    r = engine.cva(cva, n, prec, seed)
+    assert r == m.finalize(p, oracle.accumulate(got, p))
+    if prec == "f64":
+        r = engine.cva(cva, 1 << 18, prec, seed)
+        _, keep = oracle.cva_grid(1.0, n_dates, prec)
+        closed = oracle.cva_closed_form(100, 100, 0.05, 0.2, 1.0, 0.03, 0.6, n_dates, keep)
+        assert abs(r.Expected - closed) < 4 * r.std_error + 1e-6
+    # a short grid right after it: the constant-table path is untouched by the long one
+    short = m.CVA(0.03, 0.6, m.OptionData(100.0, 100.0, 0.05, 0.2, 1.0), 50)
+    a = engine.cva(short, 4096, prec, seed)
+    b = engine.price_batch([("cva", short, 4096, prec), ("cva", cva, 512, prec), ("cva", short, 4096, prec)], seed)
+    assert b[0] == a and b[2] == a and b[1] == engine.cva(cva, 512, prec, seed)
+
+
 # ------------------------------------------------------------------------------------------------
 # prices: closed forms, golden fixtures, reference GPU kernels
 # ------------------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ enum {
     MCB200_ERR_CUDA = 2,        /* a CUDA runtime call failed; see mcb200_last_error() */
     MCB200_ERR_NO_DEVICE = 3,   /* no CUDA device / device index out of range */
     MCB200_ERR_OVERFLOW = 4,    /* a partial sum left the 160-bit fixed-point window, or was NaN */
-    MCB200_ERR_UNSUPPORTED = 5, /* e.g. basket wider than MCB200_MAX_ASSETS */
+    MCB200_ERR_UNSUPPORTED = 5, /* e.g. basket wider than MCB200_MAX_ASSETS, grid longer than MCB200_MAX_DATES */
     MCB200_ERR_ALIGNMENT = 6,   /* shard boundary not on a chunk boundary */
     MCB200_ERR_PEER_TIMEOUT = 7 /* a peer rank's partial sums did not arrive in time (fused combine), or were pulled too late */
 };
@@ -42,7 +42,7 @@ enum {
 enum { MCB200_F32 = 0, MCB200_F64 = 1 };
 enum { MCB200_VANILLA = 1, MCB200_BASKET = 2, MCB200_CVA = 3 };
 
-#define MCB200_MAX_ASSETS 64
+#define MCB200_MAX_ASSETS 256 /* up to 64 assets: accumulators in registers (tensor cores for wide fp32); beyond: a generic route */
 #define MCB200_MAX_DATES (1 << 20) /* exposure dates of a CVA grid (up to 1024 kept dates sit in constant memory, longer grids in device memory) */
 #define MCB200_LANES 5
 /* accumulator block: [0..4] sum limbs, [5..9] sum-of-squares limbs, [10] paths counted,

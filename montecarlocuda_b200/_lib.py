@@ -15,7 +15,7 @@ F32, F64 = 0, 1
 VANILLA, BASKET, CVA = 1, 2, 3
 ACC_WORDS = 12
 LANES = 5
-MAX_ASSETS = 64
+MAX_ASSETS = 256
 MAX_DATES = 1 << 20
 
 

@@ -268,7 +268,7 @@ int make_basket_job(const mcb200_basket_t *o, uint64_t seed, BasketTables *t)
     const int n = o->n;
     if (n < 1)
         return MCB200_ERR_INVALID;
-    if (n > MCB200_MAX_ASSETS || basket_padded_width(n) == 0)
+    if (n > MCB200_MAX_ASSETS || n > basket_max_width())
         return MCB200_ERR_UNSUPPORTED;
     if (!finite_all({o->k, o->t, o->r}) || o->t < 0)
         return MCB200_ERR_INVALID;

@@ -459,6 +459,84 @@ struct Basket {
     }
 };
 
+// ---- baskets wider than the widest register template (64 < n <= kBasketWideMax) ----
+// The reference's N is a compile-time macro with no upper bound (DP/MonteCarlo.h:16); its kernel keeps g[], bt[], s[] in
+// local memory whatever N is.  Here only baskets beyond 64 assets take a generic route: the path's normals
+// go to a local-memory array once, and the column sweep runs over row blocks of kBasketWideRows accumulators in registers
+// -- per block: z_j from local memory, kBasketWideRows factor entries per column from a device-memory table laid out in
+// exactly that order (uniform 16-byte loads).  Same summation order as the register templates (columns 0, 1, 2, ... into
+// each exponent, assets 0, 1, 2, ... into the payoff), so a narrow basket forced through this kernel gives their bits.
+constexpr int kBasketWideMax = 256;
+constexpr int kBasketWideRows = 16;
+
+template <typename RealT, bool kAccumLayout = false>
+struct BasketWide {
+    using Real = RealT;
+    static constexpr int kUnitPaths = 1;
+    static constexpr int kUnroll = 1;
+    static constexpr int kSubBlocks = (kAccumLayout && sizeof(RealT) == 8) ? 2 : 1;
+    static constexpr int kMinBlocks = kSubBlocks > 1 ? 1 : 2;
+    static constexpr int kNpb = NormalsPerBlock<RealT>::value;
+    static constexpr int kRows = kBasketWideRows;
+    struct Params {
+        PhiloxKeys keys;
+        int n_blocks;        // row blocks: ceil(n / kRows)
+        int full;            // the factor has entries above the diagonal: every block sweeps all columns
+        const Real *table;   // device memory, see fill_wide_table
+        Real k;
+    };
+    using Shared = std::conditional_t<kAccumLayout, typename SharedAccumFor<Real>::type, typename SharedFor<Real>::type>;
+    using JobState = typename JobStateFor<Real>::type;
+    static constexpr bool kClampAtZero = sizeof(Real) == 8;
+    static __device__ __forceinline__ void prepare(const Params &, JobState &job, int tid) { prepare_polar(polar_scale<Real>(1.0), job, tid); }
+    static __device__ __forceinline__ void eval(const Params &P, uint32_t path_lo, uint32_t path_hi, Real (&v)[1], const Shared &sh,
+                                                const JobState &job)
+    {
+        const int n_pad = P.n_blocks * kRows;
+        Real z[kBasketWideMax + kNpb];          // local memory: indexed at run time
+        for (int jb = 0; jb * kNpb < n_pad; jb++) {
+            uint32_t w[4];
+            philox4x32_10(path_lo, path_hi, (uint32_t)jb, kTagBasket, P.keys, w);
+            Real zz[kNpb];
+            normals_from_words(w, zz, sh, job);
+#pragma unroll
+            for (int q = 0; q < kNpb; q++)
+                z[jb * kNpb + q] = zz[q];
+        }
+        const Real *f = P.table;                // [block][column][kRows] factor entries, then a[n_pad], then m[n_pad]
+        const Real *a = P.table + wide_factor_entries(P.n_blocks, P.full != 0);
+        const Real *m = a + n_pad;
+        Real sum = -P.k;
+        for (int rb = 0; rb < P.n_blocks; rb++) {
+            Real x[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; r++)
+                x[r] = __ldg(a + rb * kRows + r);
+            const int cols = P.full ? n_pad : (rb + 1) * kRows;
+            for (int j = 0; j < cols; j++) {
+                const Real zj = z[j];
+#pragma unroll
+                for (int r = 0; r < kRows; r++)
+                    x[r] = fma(__ldg(f + r), zj, x[r]);
+                f += kRows;
+            }
+#pragma unroll
+            for (int r = 0; r < kRows; r++)
+                sum = fma(__ldg(m + rb * kRows + r), exp_scaled(x[r], sh), sum);
+        }
+        if constexpr (kClampAtZero)
+            v[0] = sum;
+        else
+            v[0] = positive_part(sum);
+    }
+    static __host__ __device__ constexpr size_t wide_factor_entries(int n_blocks, bool full)
+    {
+        // triangular: block rb sweeps columns 0 .. (rb + 1) kRows - 1
+        return full ? (size_t)n_blocks * (size_t)(n_blocks * kRows) * kRows
+                    : (size_t)kRows * kRows * ((size_t)n_blocks * (size_t)(n_blocks + 1) / 2);
+    }
+};
+
 }  // namespace mcb
 
 #include "basket_tc.cuh"
@@ -546,9 +624,10 @@ int basket_engine_get()
 }
 void basket_engine_set(int engine) { g_basket_engine.store(engine == 1 ? 1 : 0); }
 
+static bool basket_takes_wide_route(int n);
 bool basket_uses_tensor_cores(int precision, int n)
 {
-    return precision == 0 && n > 32 && n <= kTcWidth && basket_engine_get() == 0;
+    return precision == 0 && n > 32 && n <= kTcWidth && basket_engine_get() == 0 && !basket_takes_wide_route(n);
 }
 
 static void fill_tc_table(const BasketJob &job, BasketTcTable &T)
@@ -600,6 +679,104 @@ static cudaError_t launch_tc(const BasketJob &job, const Geometry *geom, int gri
     return e;
 }
 
+// ---- host side of the wide route: the table image in the kernel's order, one growable device buffer per device ----
+static TableLock g_basket_wide_lock;
+static void *g_basket_wide_buffer[TableLock::kMaxDevices] = {};
+static size_t g_basket_wide_capacity[TableLock::kMaxDevices] = {};
+
+template <typename Real>
+static std::vector<Real> fill_wide_table(const BasketJob &job, int n_blocks)
+{
+    using W = BasketWide<Real>;
+    const double unit = ExpUnit<Real>::value;
+    const int rows = W::kRows, n_pad = n_blocks * rows;
+    std::vector<Real> t;
+    t.reserve(W::wide_factor_entries(n_blocks, job.full) + 2 * (size_t)n_pad);
+    for (int rb = 0; rb < n_blocks; rb++) {
+        const int cols = job.full ? n_pad : (rb + 1) * rows;
+        for (int j = 0; j < cols; j++)
+            for (int r = 0; r < rows; r++) {
+                const int i = rb * rows + r;
+                const bool inside = i < job.n && j < job.n && (job.full || j <= i);
+                t.push_back((Real)(inside ? job.factor[(size_t)i * job.n + j] * unit : 0.0));
+            }
+    }
+    for (int i = 0; i < n_pad; i++)
+        t.push_back((Real)(i < job.n ? job.a[i] * unit : 0.0));
+    for (int i = 0; i < n_pad; i++)
+        t.push_back((Real)(i < job.n ? job.m[i] : 0.0));      // padding assets: weight 0, exactly 0 contribution
+    return t;
+}
+
+template <typename Real>
+static cudaError_t launch_wide_t(const BasketJob &job, const Geometry *geom, int grid, unsigned long long *d_acc,
+                                 unsigned long long first_unit, unsigned long long n_units, void *d_out, cudaStream_t stream,
+                                 const LaunchOptions &opt)
+{
+    const int n_blocks = (job.n + kBasketWideRows - 1) / kBasketWideRows;
+    const std::vector<Real> staging = fill_wide_table<Real>(job, n_blocks);
+    const size_t bytes = staging.size() * sizeof(Real);
+    TableUse use(g_basket_wide_lock, stream, staging.data(), bytes);
+    if (use.status() != cudaSuccess)
+        return use.status();
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess)
+        return e;
+    if (g_basket_wide_capacity[device] < bytes) {
+        use.invalidate();   // (cudaFree waits for everything that may still read the old buffer)
+        if (g_basket_wide_buffer[device])
+            cudaFree(g_basket_wide_buffer[device]);
+        g_basket_wide_buffer[device] = nullptr;
+        g_basket_wide_capacity[device] = 0;
+        e = cudaMalloc(&g_basket_wide_buffer[device], bytes);
+        if (e != cudaSuccess)
+            return e;
+        g_basket_wide_capacity[device] = bytes;
+    }
+    if (use.needs_upload()) {
+        e = cudaMemcpyAsync(g_basket_wide_buffer[device], staging.data(), bytes, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) {
+            use.invalidate();
+            return e;
+        }
+        use.uploaded();
+    }
+    auto params = [&](auto tag) {
+        typename decltype(tag)::Params p;
+        p.keys = job.keys;
+        p.n_blocks = n_blocks;
+        p.full = job.full ? 1 : 0;
+        p.table = static_cast<const Real *>(g_basket_wide_buffer[device]);
+        p.k = (Real)job.k;
+        return p;
+    };
+    if (geom) {
+        using W = BasketWide<Real, true>;
+        e = accumulate_launch<W>(grid, params(W{}), *geom, d_acc, stream, opt);
+    } else {
+        using W = BasketWide<Real, false>;
+        const unsigned long long blocks = (n_units + kThreads - 1) / kThreads;
+        mc_paths_kernel<W><<<(int)(blocks < 65535ull ? blocks : 65535ull), kThreads, 0, stream>>>(params(W{}), first_unit, n_units, (Real *)d_out);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess)
+        use.invalidate();
+    return e;
+}
+
+// MCB200_BASKET_WIDE=1 sends every basket through the wide route (tests: its bits against the register templates')
+static bool basket_takes_wide_route(int n)
+{
+    static const bool forced = [] {
+        const char *env = std::getenv("MCB200_BASKET_WIDE");
+        return env && env[0] == '1';
+    }();
+    return n > 64 || forced;
+}
+
+int basket_max_width() { return kBasketWideMax; }
+
 int basket_padded_width(int n)
 {
     static const int widths[] = {3, 4, 8, 10, 16, 32, 64};
@@ -647,6 +824,8 @@ int basket_padded_width(int n)
 
 int basket_blocks_per_sm(int precision, int n, bool full)
 {
+    if (basket_takes_wide_route(n))
+        return precision ? accumulate_blocks_per_sm<BasketWide<double, true>>() : accumulate_blocks_per_sm<BasketWide<float, true>>();
     if (basket_uses_tensor_cores(precision, n))
         return 1;  // one CTA per SM: four tiles = all 512 tensor-memory columns
 
@@ -661,6 +840,9 @@ cudaError_t basket_launch(int precision, const BasketJob &job, const Geometry &g
 {
     const int n = job.n;
     const bool full = job.full;
+    if (basket_takes_wide_route(n))
+        return precision ? launch_wide_t<double>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream, opt)
+                         : launch_wide_t<float>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream, opt);
     if (basket_uses_tensor_cores(precision, n))
         return full ? launch_tc<true>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream, opt)
                     : launch_tc<false>(job, &geom, grid, d_acc, 0ull, 0ull, nullptr, stream, opt);
@@ -675,6 +857,9 @@ cudaError_t basket_paths(int precision, const BasketJob &job, unsigned long long
 {
     const int n = job.n;
     const bool full = job.full;
+    if (basket_takes_wide_route(n))
+        return precision ? launch_wide_t<double>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream, LaunchOptions())
+                         : launch_wide_t<float>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream, LaunchOptions());
     if (basket_uses_tensor_cores(precision, n))
         return full ? launch_tc<true>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream, LaunchOptions())
                     : launch_tc<false>(job, nullptr, 0, nullptr, first_unit, n_units, d_out, stream, LaunchOptions());

@@ -66,7 +66,8 @@ struct BasketJob {
     const double *m;       // w_i s_i
     double k;
 };
-int basket_padded_width(int n);  // template width that serves n assets, 0 if unsupported
+int basket_padded_width(int n);  // register-template width that serves n assets, 0 beyond the widest one (64)
+int basket_max_width();           // widest basket any route prices (the wide route: local-memory normals, device-memory factor)
 int basket_blocks_per_sm(int precision, int n, bool full);
 // which kernel serves wide fp32 baskets (32 < n <= 64): 0 = tensor cores (tcgen05, basket_tc.cuh), 1 = FFMA2 only.
 // Process-wide; first read falls back to the environment variable MCB200_BASKET_ENGINE (0 / 1).

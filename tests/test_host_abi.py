@@ -27,7 +27,7 @@ def test_core_library_exports_every_declared_symbol(ensure_built):
     assert set(_lib.exported_symbols()) == set(names)      # the Python binding covers the whole header
 
 
-@pytest.mark.parametrize("lib_name", ["libmcb200_dp.so", "libmcb200_sp.so", "libmcb200_dp_n10.so", "libmcb200_sp_n64.so"])
+@pytest.mark.parametrize("lib_name", ["libmcb200_dp.so", "libmcb200_sp.so", "libmcb200_dp_n10.so", "libmcb200_sp_n64.so", "libmcb200_dp_n100.so"])
 def test_dropin_libraries_export_the_reference_symbols(ensure_built, lib_name):
     lib = C.CDLL(str(ROOT / "montecarlocuda_b200" / "lib" / lib_name))
     names = [n for n in declared_functions(ROOT / "include" / "MonteCarlo.h") if n.startswith("dev_")]

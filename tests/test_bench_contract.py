@@ -26,7 +26,7 @@ def test_build_manifest_describes_the_library(ensure_built, bench):
     assert manifest is not None, why
     kernels = manifest["kernel_sass_sha256"]
     for k in ("mc_accumulate_kernel<Vanilla<double,2,1,1>>", "mc_accumulate_kernel<Vanilla<float,8,1,1>>", "mc_accumulate_kernel<Basket<double,10,0,1>>",
-              "mc_accumulate_kernel<Cva<double,1>>", "basket_tc_accumulate_kernel<0>", "mc_accumulate_batch_kernel<Cva<double,1>>"):
+              "mc_accumulate_kernel<Cva<double,1,0>>", "basket_tc_accumulate_kernel<0>", "mc_accumulate_batch_kernel<Cva<double,1,0>>"):
         assert len(kernels[k]) == 64, k
     from montecarlocuda_b200 import build
     assert manifest["source_sha256"] == build.source_hash()      # the library in the tree was built from the sources in the tree

@@ -446,8 +446,8 @@ def test_invalid_arguments_fail_loudly(engine):
     with pytest.raises(m.Mcb200Error):
         engine.vanilla(m.OptionData(float("nan"), 100, 0.05, 0.2, 1.0), 1000)
     with pytest.raises(m.Mcb200Error):
-        engine.cva(m.CVA(0.03, 0.6, VAN, 5000), 1000)
-    n = 65
+        engine.cva(m.CVA(0.03, 0.6, VAN, (1 << 20) + 1), 1000)      # MCB200_MAX_DATES
+    n = 257                                                         # MCB200_MAX_ASSETS + 1
     with pytest.raises(m.Mcb200Error):
         engine.basket(m.MultiOptionData([100.0] * n, [0.2] * n, np.eye(n), [0.0] * n, [1 / n] * n, 100.0, 1.0, 0.05), 1000)
     with pytest.raises(m.Mcb200Error):

@@ -497,7 +497,7 @@ mc_accumulate_kernel(const __grid_constant__ typename W::Params P, const __grid_
     using Real = typename W::Real;
     constexpr int kSub = W::kSubBlocks;
     pdl_launch_dependents();
-    // W::Shared in dynamic shared memory (the replicated fp64 tables are 96 KB); nothing for fp32
+    // W::Shared in dynamic shared memory (the replicated fp64 tables are 192 KB); nothing for fp32
     extern __shared__ __align__(16) unsigned char mcb_dynamic_smem[];
     typename W::Shared &sh = *reinterpret_cast<typename W::Shared *>(mcb_dynamic_smem);
     __shared__ BlockScratch scs[kSub];

@@ -155,7 +155,7 @@ struct SharedFactor64 : SharedTables64Rep {
 };
 // Wide fp64 baskets (two-pass sweep, see Basket::eval_two_pass): the plain math tables with the coarse angle table
 // next to them, plus one slot per thread and sub-block for each normal of the first half ([normal][thread]: consecutive
-// threads, conflict-free 8-byte accesses).  10 KB + 64 KB + 2 x 64 KB; the replicated tables (160 KB) would not fit
+// threads, conflict-free 8-byte accesses).  14 KB + 64 KB + 2 x 64 KB; the replicated tables (192 KB) would not fit
 // next to the slots.
 template <int kHalf>
 struct SharedTwoPass64 {

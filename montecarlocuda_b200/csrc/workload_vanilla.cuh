@@ -17,8 +17,10 @@ constexpr uint32_t kVanillaTag = 1u;
 // tuned on B200 (profiles/r01_tune_vanilla.txt): CTAs per SM / unroll of the unit loop
 template <typename Real> struct VanillaTuning;
 template <> struct VanillaTuning<float> { static constexpr int kMinBlocks = 8, kUnroll = 1; };
-// fp64: sub-blocks of 256 threads per CTA around one replicated table set (96 KB).  3 sub-blocks leave 80 registers
-// per thread and the kernel spills (11.5 ms); 2 leave 128 (94 used): 9.70 ms (profiles/r01k_tune_vanilla.txt)
+// fp64: sub-blocks of 256 threads per CTA around one replicated table set (192 KB).  2 sub-blocks (128 registers
+// available, 74 used) against 3 (80 available): 8.38 vs 9.36 ms without a spill, 10.16 ms with the round's first
+// kernel, which spilled (profiles/r02k_ab_experiments.txt) -- the kernel lives on instruction-level parallelism, not
+// on warps.  Unroll 2: 8.56 vs 8.42 ms.
 #ifndef MCB_VANILLA_UNROLL
 #define MCB_VANILLA_UNROLL 1
 #endif

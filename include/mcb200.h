@@ -236,8 +236,8 @@ int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint3
  * fn 0 = -2 ln(u), 1 = sqrt, 2 = 1/x, 3 = e^x, 4 = cos and sin of 2 pi k / 2^52 (the input's bit
  * pattern is the 52-bit integer k), 5 = the same for a 20-bit k (two-level table; k = low word of the
  * input's bit pattern), 6 = sqrt by the short iteration the pricing kernels use, 7 = 2^(y/256) (the exponential
- * with its argument in table units, as the pricing kernels call it).  out_host receives 2 doubles per element
- * (second = sin for fn 4, 5). */
+ * with its argument in table units, as the pricing kernels call it), 8 = its second variant (table entry last).
+ * out_host receives 2 doubles per element (second = sin for fn 4, 5). */
 int mcb200_debug_math64(mcb200_ctx *ctx, int fn, uint64_t n, const double *in_host, double *out_host);
 /* reduce ONE chunk of given per-path values with the pricing kernels' block reduction and
  * integer split; acc_host receives the accumulator block */

@@ -329,8 +329,8 @@ __device__ __forceinline__ float positive_part(float x) { return fmaxf(x, 0.0f);
 template <typename Real> struct ExpUnit;
 template <> struct ExpUnit<float> { static constexpr double value = 1.4426950408889634074; };           // 1 / ln 2
 template <> struct ExpUnit<double> { static constexpr double value = 369.32993046757463228; };           // 256 / ln 2
-template <class Sh> __device__ __forceinline__ float exp_scaled(float x, const Sh &) { return mufu_ex2(x); }
-template <class Sh> __device__ __forceinline__ double exp_scaled(double y, const Sh &sh) { return exp_units(y, sh.t); }
+template <bool kLateTable = false, class Sh> __device__ __forceinline__ float exp_scaled(float x, const Sh &) { return mufu_ex2(x); }
+template <bool kLateTable = false, class Sh> __device__ __forceinline__ double exp_scaled(double y, const Sh &sh) { return exp_units<kLateTable>(y, sh.t); }
 __device__ __forceinline__ float rcp_real(float x) { return mufu_rcp(x); }
 __device__ __forceinline__ double rcp_real(double x) { return rcp_newton(x); }
 

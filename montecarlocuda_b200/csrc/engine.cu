@@ -1454,7 +1454,7 @@ int mcb200_debug_normals(mcb200_ctx *ctx, int precision, uint64_t n, const uint3
 
 int mcb200_debug_math64(mcb200_ctx *ctx, int fn, uint64_t n, const double *in_host, double *out_host)
 {
-    if (!ctx || !in_host || !out_host || n == 0 || fn < 0 || fn > 7)
+    if (!ctx || !in_host || !out_host || n == 0 || fn < 0 || fn > 8)
         return MCB200_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     DeviceGuard guard(ctx->device);

@@ -240,7 +240,7 @@ struct Basket {
     static constexpr bool kClampAtZero = sizeof(Real) == 8;   // fp64: add_value clamps the payoff (device_common.cuh)
     static __device__ __forceinline__ void prepare(const Params &, JobState &job, int tid) { prepare_polar(polar_scale<Real>(1.0), job, tid); }
     // exponents are kept in the units of exp_scaled (fill_table): log2 units for fp32, units of ln2/256 for fp64
-    template <class Sh> static __device__ __forceinline__ Real grow(Real x, const Sh &sh) { return exp_scaled(x, sh); }
+    template <class Sh> static __device__ __forceinline__ Real grow(Real x, const Sh &sh) { return exp_scaled<true>(x, sh); }
     static __device__ __forceinline__ Real clamp(Real payoff)
     {
         if constexpr (kClampAtZero)
@@ -522,7 +522,7 @@ struct BasketWide {
             }
 #pragma unroll
             for (int r = 0; r < kRows; r++)
-                sum = fma(__ldg(m + rb * kRows + r), exp_scaled(x[r], sh), sum);
+                sum = fma(__ldg(m + rb * kRows + r), exp_scaled<true>(x[r], sh), sum);
         }
         if constexpr (kClampAtZero)
             v[0] = sum;

@@ -119,13 +119,13 @@ struct Cva {
                                                 Real &cva, const Shared &sh)
     {
         y = fma(sr, trig, y + P.mu_dt);
-        const Real s = exp_scaled(y, sh);
+        const Real s = exp_scaled<true>(y, sh);
         const Real d1 = fma(y, D.inv, D.c1);
         const Real d2 = d1 - D.sig;
         // sqrt(2 pi) s phi(d1) = sqrt(2 pi) kd phi(d2) = e^{y - d1^2/2}.  The exponent can be -1e14 (a date a few ulps
         // before maturity) or -inf (exact grid, tau = 0): floor it where e^x is already 0 for every purpose, so the
         // table-driven exp stays in range
-        const Real a = exp_scaled(floor_exponent(fma(P.half_unit * d1, d1, y)), sh);
+        const Real a = exp_scaled<true>(floor_exponent(fma(P.half_unit * d1, d1, y)), sh);
         Real k1, p1, k2, p2;
         hastings_factors(d1, k1, p1);
         hastings_factors(d2, k2, p2);

@@ -80,7 +80,7 @@ debug_reduce_kernel(const double *__restrict__ values, unsigned long long n_vali
 // The fp64 special functions on their own: fn 0 = -2 ln(u), 1 = sqrt, 2 = 1/x, 3 = e^x,
 // 4 = cos/sin of 2 pi k / 2^52 (input reinterpreted as the 52-bit integer k; two outputs),
 // 5 = cos/sin of 2 pi k / 2^20 from the two-level table (k = low word of the input), 6 = sqrt (short iteration),
-// 7 = 2^(y/256) (exp_units).
+// 7 = 2^(y/256) (exp_units), 8 = the same with the table entry entering last (exp_units<true>: basket, CVA).
 __global__ void debug_math64_kernel(int fn, unsigned long long n, const double *__restrict__ in,
                                     double *__restrict__ out)
 {
@@ -96,6 +96,7 @@ __global__ void debug_math64_kernel(int fn, unsigned long long n, const double *
         switch (fn) {
             case 0: a = neg2log_unit(x, sh.t, job); break;
             case 7: a = exp_units(x, sh.t); break;
+            case 8: a = exp_units<true>(x, sh.t); break;
             case 1: a = sqrt_pos(x); break;
             case 6: a = sqrt_pos<true>(x); break;
             case 2: a = rcp_newton(x); break;

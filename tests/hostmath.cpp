@@ -42,6 +42,7 @@ void hm_scaled_log(const double *u, double k, double k_ln2, double *out, long n)
     for (long i = 0; i < n; i++) out[i] = scaled_log_unit(u[i], tables(), k, s);
 }
 void hm_exp_units(const double *y, double *out, long n) { for (long i = 0; i < n; i++) out[i] = exp_units(y[i], tables()); }
+void hm_exp_units_late(const double *y, double *out, long n) { for (long i = 0; i < n; i++) out[i] = exp_units<true>(y[i], tables()); }
 void hm_sqrt(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = sqrt_pos(x[i]); }
 void hm_sqrt_short(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = sqrt_pos<true>(x[i]); }
 void hm_rcp(const double *x, double *out, long n) { for (long i = 0; i < n; i++) out[i] = rcp_newton(x[i]); }

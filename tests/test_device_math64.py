@@ -45,6 +45,7 @@ def check(run):
     y = np.concatenate([c["exp"] * 369.3299304675746, np.array([0.0, 0.5, -0.5, 1.5, 255.5, 256.0, -258000.0, 258000.0]),
                         np.arange(-600.0, 600.0, 0.25)])
     assert ulps(run(7, y)[:, 0], np.exp2(y.astype(np.longdouble) / 256).astype(np.float64)).max() <= 2
+    assert ulps(run(8, y)[:, 0], np.exp2(y.astype(np.longdouble) / 256).astype(np.float64)).max() <= 2      # table entry last
     assert ulps(run(1, c["sqrt"])[:, 0], np.sqrt(c["sqrt"])).max() <= 2
     assert ulps(run(6, c["sqrt"])[:, 0], np.sqrt(c["sqrt"])).max() <= 2      # short iteration (basket, CVA kernels)
     assert ulps(run(2, c["rcp"])[:, 0], 1.0 / c["rcp"]).max() <= 2
@@ -75,7 +76,7 @@ def hostmath(tmp_path_factory):
 
 
 def test_host_build_of_device_math(hostmath):
-    names = {0: "hm_neg2log", 1: "hm_sqrt", 2: "hm_rcp", 3: "hm_exp", 6: "hm_sqrt_short", 7: "hm_exp_units"}
+    names = {0: "hm_neg2log", 1: "hm_sqrt", 2: "hm_rcp", 3: "hm_exp", 6: "hm_sqrt_short", 7: "hm_exp_units", 8: "hm_exp_units_late"}
 
     def run(fn, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -230,8 +230,8 @@ template <class Tab> MCB_FN void sincos_turn20(uint32_t k, double &cs, double &s
     double ch, sh, cl, sl;
     T.turn_hi_entry(k, ch, sh);
     T.turn_lo_entry(k, cl, sl);
-    cs = fma_(-sh, sl, ch * cl);
-    sn = fma_(ch, sl, sh * cl);
+    cs = fma_(ch, cl, -(sh * sl));
+    sn = fma_(sh, cl, ch * sl);
 }
 
 // ---- k ln(u) for u in [2^-63, 1] and a caller-chosen k ---------------------------------------------

@@ -34,8 +34,8 @@ struct SharedTables64Rep {
     {
         for (int i = threadIdx.x; i < kLogEntries * 8; i += blockDim.x) {
             const int j = i >> 3, rep = i & 7;
-            t.log_rep[j][rep][0] = bias_log_recip(log_table_entry(j)[0]);
-            t.log_rep[j][rep][1] = log_table_entry(j)[1];
+            t.log_rep[j][rep][0] = bias_log_recip(kLogTable[j][0]);
+            t.log_rep[j][rep][1] = kLogTable[j][1];
         }
         for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
             const int j = i >> 4, rep = i & 15;

@@ -3,7 +3,7 @@
 // libdevice's log / sincospi / exp / division cost 30 / 27 / 18 / 8+ fp64 instructions plus as many
 // integer ones (measured: 162 warp-instructions per vanilla path, profiles/r01a_*).  Here:
 //
-//   scaled_log_unit  k ln(u), u in (0,1]  table of 256 reciprocals (shared memory) + degree-6 log1p; the exponent's
+//   scaled_log_unit  k ln(u), u in (0,1]  table of 512 reciprocals (shared memory) + degree-5 log1p; the exponent's
 //                                          share comes from a 64-entry table per job (LogScale64)          9 fp64
 //   sqrt_pos         sqrt(x)               MUFU.RSQ64H seed + 2 coupled Newton steps (or 1 + a correction) 7 / 5 fp64
 //   sincos_turn20    cos/sin(2 pi k/2^20)  two-level table (12 + 8 bits) and the addition theorems         4 fp64
@@ -102,13 +102,10 @@ MCB_FN uint32_t and_or(uint32_t a, uint32_t mask, uint32_t c)
 MCB_FN double bias_log_recip(double c) { return make_double(hi_word(c) + 0x3ff00000, lo_word(c)); }
 MCB_FN double bias_exp_entry(double t, int j) { return make_double(hi_word(t) - (j << 12), lo_word(t)); }
 
-// index bits of the logarithm's table: 8 -> 256 entries and a degree-6 log1p, 9 -> 512 entries and degree 5
-#ifndef MCB_LOG_BITS
-#define MCB_LOG_BITS 9
-#endif
-constexpr int kLogBits = MCB_LOG_BITS;
+// index bits of the logarithm's table: 512 entries and a degree-5 log1p (256 and degree 6 until round 2: one fp64
+// instruction more per Box-Muller pair, profiles/r02k_ab_experiments.txt 3)
+constexpr int kLogBits = 9;
 constexpr int kLogEntries = 1 << kLogBits;
-MCB_FN const double *log_table_entry(int i) { return kLogBits == 9 ? kLogTable9[i] : kLogTable[i & 255]; }
 
 // Plain layout: host build, instrumentation and per-path kernels (their coarse angle table stays where the
 // generated one lies -- global memory on the device: 64 KB do not fit a static shared-memory allocation).
@@ -116,7 +113,7 @@ struct Tables64 {
     double log_tab[kLogEntries][2];       // { c_i (biased), -ln c_i }
     double exp_tab[256];          // 2^(j/256) (biased)
     double turn_lo[256][2];       // { cos, sin } of 2 pi j / 2^20
-    // hi_u = high word of u: the entry of its top 8 mantissa bits
+    // hi_u = high word of u: the entry of its top kLogBits mantissa bits
     MCB_MEMBER void log_entry(int hi_u, double &c, double &l) const
     {
         const int i = (hi_u >> (20 - kLogBits)) & (kLogEntries - 1);
@@ -130,8 +127,8 @@ struct Tables64 {
     MCB_MEMBER void fill(int i)   // for every i < 256
     {
         for (int j = i; j < kLogEntries; j += 256) {
-            log_tab[j][0] = bias_log_recip(log_table_entry(j)[0]);
-            log_tab[j][1] = log_table_entry(j)[1];
+            log_tab[j][0] = bias_log_recip(kLogTable[j][0]);
+            log_tab[j][1] = kLogTable[j][1];
         }
         exp_tab[i] = bias_exp_entry(kExpTable[i], i);
         turn_lo[i][0] = kTurnLoTable[i][0];
@@ -235,8 +232,8 @@ template <class Tab> MCB_FN void sincos_turn20(uint32_t k, double &cs, double &s
 }
 
 // ---- k ln(u) for u in [2^-63, 1] and a caller-chosen k ---------------------------------------------
-// u = 2^e m, m in [1,2); i = top 8 mantissa bits; r = m c_i - 1 = u (c_i 2^-e) - 1 in [0, 2^-8);
-// ln u = e ln2 + (-ln c_i) + log1p(r), log1p by its degree-6 Taylor polynomial (|error| < 2^-59).
+// u = 2^e m, m in [1,2); i = top 9 mantissa bits; r = m c_i - 1 = u (c_i 2^-e) - 1 in [0, 2^-9);
+// ln u = e ln2 + (-ln c_i) + log1p(r), log1p by its degree-5 Taylor polynomial (|error| < 2^-56).
 // The scale k rides on the constants of the last two FMAs and on the job's exponent table S (LogScale64, filled
 // with k ln 2), so e.g. b^2 (-2 ln u) -- the squared radius of a Box-Muller pair already multiplied by a diffusion
 // scale b -- costs the same 9 fp64 instructions as -2 ln u (k = -2).
@@ -249,13 +246,7 @@ template <class Tab> MCB_FN double scaled_log_unit(double u, const Tab &T, doubl
     double c, l;
     T.log_entry(hi, c, l);
     const double r = fma_(u, make_double(hi_word(c) - ebits, lo_word(c)), -1.0);
-    double q;
-    if (kLogBits == 9) {
-        q = fma_(r, 0.2, -0.25);                           // r < 2^-9: r^6/6 < 2^-56
-    } else {
-        q = fma_(r, -1.0 / 6.0, 0.2);
-        q = fma_(r, q, -0.25);
-    }
+    double q = fma_(r, 0.2, -0.25);                        // r < 2^-9: r^6/6 < 2^-56
     q = fma_(r, q, 1.0 / 3.0);
     q = fma_(r, q, -0.5);
     const double p = fma_(r * r, q, r);                    // log1p(r)

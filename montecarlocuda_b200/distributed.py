@@ -102,17 +102,33 @@ def _exchange_over_process_group(group):
     return exchange
 
 
+def agree_on_status(status: int, group=None, device=None) -> int:
+    """The worst status any rank of the group saw (one MAX all-reduce of a 4-byte word): every rank gets the same
+    answer, so a failure only SOME ranks observed -- e.g. a peer that launched after the others' mailbox timeout --
+    becomes a failure of the job on all of them instead of a diverging program."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(status)
+    word = torch.tensor([int(status)], dtype=torch.int32, device=device if device is not None else "cpu")
+    dist.all_reduce(word, op=dist.ReduceOp.MAX, group=group)
+    return int(word.item())
+
+
 class ShardedPricer:
     """One rank's view of a sharded pricing job: persistent engine + device accumulator.
     combine = "peer": the cross-GPU sum runs inside the pricing kernel over peer memory (peer_mode "push": split phase,
     "wait": single phase); "nccl": one all-reduce after it; "auto": peer when the group has more than one rank,
     falling back to nccl (with the reason kept in `combine_note`) only if the peer mailboxes cannot be mapped.
-    overlap: launch with programmatic dependent launch, so that back-to-back jobs overlap tail and start."""
+    overlap: launch with programmatic dependent launch, so that back-to-back jobs overlap tail and start.
+    agree_on_errors: result() ends with one tiny MAX all-reduce of the ranks' status words, so that an error only some
+    ranks saw (a peer timeout) is raised on every rank; off by default -- it puts a collective back behind every job."""
 
     RING = 32
 
     def __init__(self, engine: Engine | None = None, device: int | None = None, group=None, combine: str = "auto",
-                 peer_mode: str = "push", overlap: bool = True):
+                 peer_mode: str = "push", overlap: bool = True, agree_on_errors: bool = False):
         import torch
 
         if device is None:
@@ -122,6 +138,7 @@ class ShardedPricer:
         self.engine = engine or Engine(device)
         self.engine.set_overlap(overlap)
         self.group = group
+        self.agree_on_errors = agree_on_errors
         # a ring of accumulator blocks zeroed in one memset every RING steps (no memset kernel per step)
         self.ring = torch.zeros((self.RING, _lib.ACC_WORDS), dtype=torch.int64, device=self.device)
         self.slot = 0
@@ -205,6 +222,20 @@ class ShardedPricer:
     def result(self, p: _lib.PlanT) -> OptionValue:
         """The combined accumulator of the LAST enqueued job: [second phase of the combine ->] device -> host copy ->
         closing formulas."""
+        if not self.agree_on_errors:
+            return self._result(p)
+        status, mine = _lib.OK, None
+        try:
+            mine = self._result(p)
+        except _lib.Mcb200Error as exc:
+            status = exc.status
+        worst = agree_on_status(status, self.group, self.device)
+        if worst != _lib.OK:
+            raise _lib.Mcb200Error(worst, "the sharded job failed on this rank" if status != _lib.OK
+                                   else "the sharded job failed on another rank of the group")
+        return mine
+
+    def _result(self, p: _lib.PlanT) -> OptionValue:
         stream = self.torch.cuda.current_stream(self.device)
         if not self._pulled:
             # the pull kernel writes the 12 words straight into the pinned host block (unified addressing: the
@@ -229,4 +260,4 @@ def price_sharded(workload: str, params, n_paths: int, precision=_lib.F64, seed:
     return pricer.price(workload, params, n_paths, _prec(precision), seed)
 
 
-__all__ = ["PeerGroup", "ShardedPricer", "combine_accumulators", "price_sharded", "OptionData", "MultiOptionData", "CVA"]
+__all__ = ["PeerGroup", "ShardedPricer", "agree_on_status", "combine_accumulators", "price_sharded", "OptionData", "MultiOptionData", "CVA"]

@@ -80,3 +80,27 @@ def _single(out_dir, n_paths, prec):
     r = m.finalize(p, acc.view(np.uint64))
     np.save(Path(out_dir) / "w1_r0.npy", np.array([r.Expected, r.Confidence, r.sum, r.sumsq, r.n_paths]))
     np.save(Path(out_dir) / "acc_w1_r0.npy", acc)
+
+
+def _status_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from montecarlocuda_b200 import _lib
+    from montecarlocuda_b200.distributed import agree_on_status
+
+    everyone_fine = agree_on_status(_lib.OK)
+    one_timed_out = agree_on_status(_lib.ERR_PEER_TIMEOUT if rank == world - 1 else _lib.OK)   # only the last rank saw it
+    np.save(Path(out_dir) / f"status_r{rank}.npy", np.array([everyone_fine, one_timed_out]))
+    dist.destroy_process_group()
+
+
+def test_ranks_agree_on_a_failure_only_one_of_them_saw(tmp_path):
+    """ShardedPricer(agree_on_errors=True): a peer timeout that one rank observed becomes the status of the job on every
+    rank (one MAX all-reduce), instead of a program whose ranks disagree on whether the job succeeded."""
+    from montecarlocuda_b200 import _lib
+    world = 3
+    mp.spawn(_status_worker, args=(world, 29500 + (os.getpid() % 2000) + 17, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(tmp_path / f"status_r{r}.npy")
+        assert list(got) == [_lib.OK, _lib.ERR_PEER_TIMEOUT]

@@ -424,6 +424,31 @@ __device__ __forceinline__ void add_value(double v, double &s, double &s2)
     s2 = fma(v, v, s2);
 }
 
+// fp32 with an even number of paths per draw unit (the European call: six): a thread keeps TWO interleaved pairs of
+// running sums -- the even paths of every unit go into one, the odd paths into the other, and one float addition joins
+// them at the end of the chunk -- so that the accumulations of two paths are ONE FADD2 and ONE FFMA2 (packed fp32,
+// sm_100) instead of two FADD and two FFMA: the fp32 call is bound by issue slots.  This order is part
+// of the stream definition; the oracle and the debug reduction restate it (orc_chunk_reduce, debug_reduce_kernel).
+struct PackedSums {
+    unsigned long long s = 0ull, s2 = 0ull;   // {even paths, odd paths} of value and of value^2
+    __device__ __forceinline__ void add(float even, float odd)
+    {
+        unsigned long long v;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(even), "f"(odd));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s) : "l"(v));
+        asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(s2) : "l"(v));
+    }
+    static __device__ __forceinline__ float joined(unsigned long long pair)
+    {
+        float even, odd;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(even), "=f"(odd) : "l"(pair));
+        return even + odd;
+    }
+};
+template <class W> struct accumulates_packed {
+    static constexpr bool value = std::is_same<typename W::Real, float>::value && W::kUnitPaths % 2 == 0 && !W::kClampAtZero;
+};
+
 // One chunk of the job: thread t owns units base + k * 256 + t for k < rounds, in that order, and accumulates value
 // and value^2 in W::Real (short runs: at most rounds * kUnitPaths <= 384 terms) before the fp64 block reduction.
 template <class W>
@@ -435,6 +460,7 @@ __device__ __forceinline__ void run_chunk(const typename W::Params &P, const Job
     const unsigned long long base = chunk * G.chunk_units;
     const unsigned long long path_end = (base + G.chunk_units) * (unsigned long long)W::kUnitPaths;
     Real s = 0, s2 = 0;
+    PackedSums packed;   // accumulates_packed<W> only
     const bool whole = path_end <= G.total_paths;
     if (whole) {
         n_valid = G.chunk_units * (unsigned long long)W::kUnitPaths;
@@ -452,9 +478,15 @@ __device__ __forceinline__ void run_chunk(const typename W::Params &P, const Job
                 break;
             Real v[W::kUnitPaths];
             W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh, job);
+            if constexpr (accumulates_packed<W>::value) {
 #pragma unroll
-            for (int q = 0; q < W::kUnitPaths; q++)
-                add_value<W::kClampAtZero>(v[q], s, s2);
+                for (int q = 0; q + 1 < W::kUnitPaths; q += 2)
+                    packed.add(v[q], v[q + 1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < W::kUnitPaths; q++)
+                    add_value<W::kClampAtZero>(v[q], s, s2);
+            }
         }
     } else {
         // the job's last chunk with several paths per unit: mask paths beyond the total
@@ -465,12 +497,24 @@ __device__ __forceinline__ void run_chunk(const typename W::Params &P, const Job
                 break;
             Real v[W::kUnitPaths];
             W::eval(P, (uint32_t)base + (uint32_t)(k * kThreads) + tid, (uint32_t)(base >> 32), v, sh, job);
+            if constexpr (accumulates_packed<W>::value) {
+                // (a path beyond the total adds +0 to its running sums: exact)
 #pragma unroll
-            for (int q = 0; q < W::kUnitPaths; q++) {
-                if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths)
-                    add_value<W::kClampAtZero>(v[q], s, s2);
+                for (int q = 0; q + 1 < W::kUnitPaths; q += 2)
+                    packed.add(unit * (unsigned long long)W::kUnitPaths + q < G.total_paths ? v[q] : Real(0),
+                               unit * (unsigned long long)W::kUnitPaths + q + 1 < G.total_paths ? v[q + 1] : Real(0));
+            } else {
+#pragma unroll
+                for (int q = 0; q < W::kUnitPaths; q++) {
+                    if (unit * (unsigned long long)W::kUnitPaths + q < G.total_paths)
+                        add_value<W::kClampAtZero>(v[q], s, s2);
+                }
             }
         }
+    }
+    if constexpr (accumulates_packed<W>::value) {
+        s = PackedSums::joined(packed.s);
+        s2 = PackedSums::joined(packed.s2);
     }
     s_out = s;
     s2_out = s2;

@@ -51,7 +51,10 @@ debug_reduce_kernel(const double *__restrict__ values, unsigned long long n_vali
     __shared__ BlockScratch sc;
     scratch_init(sc);
     double s = 0, s2 = 0;
-    float fs = 0, fs2 = 0;
+    // fp32 with an even number of paths per unit: even and odd paths of a unit in running sums of their own, joined by
+    // one float addition at the end (PackedSums, device_common.cuh); otherwise fs[1] stays 0
+    float fs[2] = {0, 0}, fs2[2] = {0, 0};
+    const bool interleaved = (unit_paths & 1) == 0;
     for (int k = 0; k < G.rounds; k++) {
         const unsigned long long unit = (unsigned long long)k * kThreads + threadIdx.x;
         for (int q = 0; q < unit_paths; q++) {
@@ -60,8 +63,9 @@ debug_reduce_kernel(const double *__restrict__ values, unsigned long long n_vali
                 continue;
             if (accumulate_in_float) {
                 const float x = (float)values[idx];
-                fs += x;
-                fs2 = fmaf(x, x, fs2);
+                const int which = interleaved ? (q & 1) : 0;
+                fs[which] += x;
+                fs2[which] = fmaf(x, x, fs2[which]);
             } else {
                 const double x = values[idx];
                 s += x;
@@ -70,8 +74,8 @@ debug_reduce_kernel(const double *__restrict__ values, unsigned long long n_vali
         }
     }
     if (accumulate_in_float) {
-        s = (double)fs;
-        s2 = (double)fs2;
+        s = (double)(fs[0] + fs[1]);
+        s2 = (double)(fs2[0] + fs2[1]);
     }
     chunk_commit(s, s2, n_valid, G, sc);
     scratch_flush(sc, acc);

@@ -230,7 +230,11 @@ void orc_chunk_reduce(const double *values, uint64_t n_valid, int unit_paths, in
     double ts[ORC_THREADS], ts2[ORC_THREADS];
     for (int tid = 0; tid < ORC_THREADS; tid++) {
         double s = 0, s2 = 0;
-        float fs = 0, fs2 = 0;
+        /* fp32 with an even number of paths per draw unit: the even and the odd paths of every unit have running sums
+         * of their own, joined by one float addition at the end of the chunk (the engine accumulates two paths per
+         * packed instruction); otherwise one running sum */
+        float fs[2] = {0, 0}, fs2[2] = {0, 0};
+        int interleaved = (unit_paths & 1) == 0;
         for (int k = 0; k < rounds; k++) {
             uint64_t unit = (uint64_t)k * ORC_THREADS + (uint64_t)tid;
             for (int q = 0; q < unit_paths; q++) {
@@ -239,8 +243,9 @@ void orc_chunk_reduce(const double *values, uint64_t n_valid, int unit_paths, in
                     continue;
                 if (accumulate_in_float) {
                     float x = (float)values[idx];
-                    fs += x;
-                    fs2 = fmaf(x, x, fs2);
+                    int which = interleaved ? (q & 1) : 0;
+                    fs[which] += x;
+                    fs2[which] = fmaf(x, x, fs2[which]);
                 } else {
                     double x = values[idx];
                     s += x;
@@ -248,8 +253,8 @@ void orc_chunk_reduce(const double *values, uint64_t n_valid, int unit_paths, in
                 }
             }
         }
-        ts[tid] = accumulate_in_float ? (double)fs : s;
-        ts2[tid] = accumulate_in_float ? (double)fs2 : s2;
+        ts[tid] = accumulate_in_float ? (double)(float)(fs[0] + fs[1]) : s;
+        ts2[tid] = accumulate_in_float ? (double)(float)(fs2[0] + fs2[1]) : s2;
     }
     /* xor butterfly inside each warp (offsets 16, 8, 4, 2, 1): every lane ends with the
      * same value, so only lane 0 is tracked */
